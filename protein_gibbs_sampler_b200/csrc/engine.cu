@@ -1,0 +1,1005 @@
+// pgibbs engine: host-side orchestration of the on-device Gibbs step + the C ABI (include/pgibbs.h).
+// One engine per GPU.  All work is queued on one CUDA stream; nothing between iterations touches the host.
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pgibbs.h"
+#include "attention.cuh"
+#include "gemm.cuh"
+#include "msa_attention.cuh"
+#include "rowwise.cuh"
+
+namespace pg {
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define TRY(call)               \
+  do {                          \
+    int _r = (call);            \
+    if (_r) return _r;          \
+  } while (0)
+
+// ------------------------------------------------------------------------- tensor maps (driver API)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp16 row-major [rows, cols] (ld elements between rows); box = 64 columns x box_rows, 128B swizzle.
+static int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld,
+                        uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(__half)};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu box=%u)",
+                                     (int)r, (unsigned long long)rows, (unsigned long long)cols,
+                                     (unsigned long long)ld, box_rows);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------- GEMM launch
+static int g_num_sms = 0;
+
+template <int BN, int EPI>
+static int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    CK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            gemm_smem_bytes(BN)));
+    configured = true;
+  }
+  const int m_tiles = (p.M + kBM - 1) / kBM, n_tiles = (p.N + BN - 1) / BN;
+  const int grid = std::min(g_num_sms, m_tiles * n_tiles);
+  gemm_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, gemm_smem_bytes(BN), st>>>(a, b, p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+template <int EPI>
+static int launch_gemm_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
+  switch (bn) {
+    case 64: return launch_gemm_inst<64, EPI>(a, b, p, st);
+    case 128: return launch_gemm_inst<128, EPI>(a, b, p, st);
+    case 192: return launch_gemm_inst<192, EPI>(a, b, p, st);
+    case 256: return launch_gemm_inst<256, EPI>(a, b, p, st);
+  }
+  return fail("unsupported GEMM block_n %d", bn);
+}
+
+static int launch_gemm(int epi, int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p,
+                       cudaStream_t st) {
+  if (p.K % kBK) return fail("GEMM K=%d must be a multiple of %d", p.K, kBK);
+  if (p.N % 16) return fail("GEMM N=%d must be a multiple of 16", p.N);
+  switch (epi) {
+    case EPI_BIAS_F16: return launch_gemm_bn<EPI_BIAS_F16>(bn, a, b, p, st);
+    case EPI_GELU_F16: return launch_gemm_bn<EPI_GELU_F16>(bn, a, b, p, st);
+    case EPI_RESID_F32: return launch_gemm_bn<EPI_RESID_F32>(bn, a, b, p, st);
+    case EPI_QKV_F16: return launch_gemm_bn<EPI_QKV_F16>(bn, a, b, p, st);
+    case EPI_GELU_F32: return launch_gemm_bn<EPI_GELU_F32>(bn, a, b, p, st);
+    case EPI_BIAS_F32: return launch_gemm_bn<EPI_BIAS_F32>(bn, a, b, p, st);
+  }
+  return fail("unsupported GEMM epilogue %d", epi);
+}
+
+// Tile width: fewest (waves x BN) on the persistent grid; ties go to the wider tile (less A re-read).
+static int pick_block_n(int M, int N, int multiple_of) {
+  static const int cands[] = {256, 192, 128, 64};
+  const int m_tiles = (M + kBM - 1) / kBM;
+  long best_cost = -1;
+  int best = 64;
+  for (int bn : cands) {
+    if (bn % multiple_of) continue;
+    const long tiles = static_cast<long>(m_tiles) * ((N + bn - 1) / bn);
+    const long waves = (tiles + g_num_sms - 1) / g_num_sms;
+    const long cost = waves * bn;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  }
+  return best;
+}
+
+// ------------------------------------------------------------------------------- small helper kernels
+__global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
+__global__ void f16_to_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i < n) out[i] = __half2float(in[i]);
+}
+__global__ void rope_table_kernel(float2* tab, int T, int half) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * half) return;
+  const int t = i / half, j = i % half;
+  // inv_freq = 1 / 10000^(2j/Dh), angle = t * inv_freq  (fair-esm rotary_embedding.py), in fp32 like torch
+  const float inv_freq = 1.0f / powf(10000.0f, static_cast<float>(2 * j) / static_cast<float>(2 * half));
+  const float ang = static_cast<float>(t) * inv_freq;
+  tab[i] = make_float2(cosf(ang), sinf(ang));
+}
+
+static int to_f16(const float* in, __half* out, long long n, cudaStream_t st) {
+  f32_to_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(in, out, n);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------- the engine
+struct LayerW {
+  // single-sequence models: attn = self_attn.  MSA: row = row_self_attention, col = column_self_attention
+  __half *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
+  float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
+  const float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
+  // MSA column attention
+  __half *c_wqkv = nullptr, *c_wo = nullptr;
+  float *c_bqkv = nullptr, *c_bo = nullptr;
+  const float *lncw = nullptr, *lncb = nullptr;
+  CUtensorMap m_wqkv, m_wo, m_w1, m_w2, m_cwqkv, m_cwo;
+};
+
+struct ProfEntry { double ms = 0; int launches = 0; };
+
+}  // namespace pg
+
+using namespace pg;
+
+struct pgibbs_engine {
+  pgibbs_model_config cfg;
+  int device = 0;
+  cudaStream_t stream = nullptr, own_stream = nullptr;
+  std::map<std::string, std::pair<float*, int64_t>> raw;  // fp32 device copies by state-dict key
+  std::vector<void*> owned;                               // packed weight allocations
+  std::vector<LayerW> L;
+  bool finalized = false;
+  __half* w_dense = nullptr;
+  float* b_dense = nullptr;
+  CUtensorMap m_wdense;
+  float2* rope = nullptr;
+  int rope_T = 0;
+  // activations
+  int B = 0, R = 0, T = 0, n_seq = 0, M = 0;
+  int32_t* tokens = nullptr;
+  float* x = nullptr;
+  __half *h = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr, *hs = nullptr;
+  float *g = nullptr, *logits = nullptr, *scores = nullptr;
+  CUtensorMap m_h, m_ctx, m_ffn, m_hs;
+  int bn_qkv = 256, bn_o = 256, bn_fc1 = 256, bn_fc2 = 256, bn_dense = 256;
+  // schedule / rng
+  int32_t* positions = nullptr;
+  int64_t positions_numel = 0, positions_used = 0;
+  int n_iters = 0, P = 0, has_dup = 0;
+  int64_t iter_stride = 0, chain_stride = 0;
+  float* noise = nullptr;
+  int64_t noise_numel = 0;
+  int noise_stride = 0;
+  uint64_t seed = 0x243F6A8885A308D3ull;
+  int32_t* valid_dev = nullptr;
+  int32_t* identity_pos = nullptr;  // 0..T-1 (forward_logits)
+  int layer_limit = -1;
+  // profiling
+  bool prof = false;
+  std::map<std::string, ProfEntry> prof_acc;
+  std::vector<std::tuple<std::string, cudaEvent_t, cudaEvent_t>> prof_pending;
+  int64_t launches = 0;
+};
+
+namespace pg {
+
+struct ProfScope {
+  pgibbs_engine* e;
+  cudaEvent_t a = nullptr, b = nullptr;
+  const char* name;
+  ProfScope(pgibbs_engine* e_, const char* n) : e(e_), name(n) {
+    e->launches++;
+    if (e->prof) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, e->stream);
+    }
+  }
+  ~ProfScope() {
+    if (e->prof) {
+      cudaEventRecord(b, e->stream);
+      e->prof_pending.emplace_back(name, a, b);
+    }
+  }
+};
+
+static int prof_flush(pgibbs_engine* e) {
+  if (e->prof_pending.empty()) return 0;
+  CK(cudaStreamSynchronize(e->stream));
+  for (auto& t : e->prof_pending) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, std::get<1>(t), std::get<2>(t));
+    auto& acc = e->prof_acc[std::get<0>(t)];
+    acc.ms += ms;
+    acc.launches++;
+    cudaEventDestroy(std::get<1>(t));
+    cudaEventDestroy(std::get<2>(t));
+  }
+  e->prof_pending.clear();
+  return 0;
+}
+
+template <typename T>
+static int dev_alloc(T** p, size_t n) {
+  *p = nullptr;
+  CK(cudaMalloc(reinterpret_cast<void**>(p), std::max<size_t>(n, 1) * sizeof(T)));
+  return 0;
+}
+
+static const float* raw_get(pgibbs_engine* e, const std::string& k, int64_t expect) {
+  auto it = e->raw.find(k);
+  if (it == e->raw.end()) { fail("missing weight tensor '%s'", k.c_str()); return nullptr; }
+  if (expect >= 0 && it->second.second != expect) {
+    fail("weight '%s' has %lld elements, expected %lld", k.c_str(), (long long)it->second.second, (long long)expect);
+    return nullptr;
+  }
+  return it->second.first;
+}
+
+// concat [q;k;v] weights -> fp16 [3d, d], biases -> fp32 [3d]
+static int pack_qkv(pgibbs_engine* e, const std::string& prefix, __half** w, float** b) {
+  const int d = e->cfg.embed_dim;
+  TRY(dev_alloc(w, static_cast<size_t>(3) * d * d));
+  TRY(dev_alloc(b, static_cast<size_t>(3) * d));
+  e->owned.push_back(*w);
+  e->owned.push_back(*b);
+  const char* names[3] = {"q_proj", "k_proj", "v_proj"};
+  for (int i = 0; i < 3; ++i) {
+    const float* ws = raw_get(e, prefix + names[i] + ".weight", static_cast<int64_t>(d) * d);
+    const float* bs = raw_get(e, prefix + names[i] + ".bias", d);
+    if (!ws || !bs) return 1;
+    TRY(to_f16(ws, *w + static_cast<size_t>(i) * d * d, static_cast<long long>(d) * d, e->stream));
+    CK(cudaMemcpyAsync(*b + static_cast<size_t>(i) * d, bs, d * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
+  }
+  return 0;
+}
+
+static int pack_linear(pgibbs_engine* e, const std::string& prefix, int n_out, int n_in, __half** w, float** b) {
+  const float* ws = raw_get(e, prefix + ".weight", static_cast<int64_t>(n_out) * n_in);
+  const float* bs = raw_get(e, prefix + ".bias", n_out);
+  if (!ws || !bs) return 1;
+  TRY(dev_alloc(w, static_cast<size_t>(n_out) * n_in));
+  e->owned.push_back(*w);
+  TRY(to_f16(ws, *w, static_cast<long long>(n_out) * n_in, e->stream));
+  *b = const_cast<float*>(bs);
+  return 0;
+}
+
+static void drop_raw(pgibbs_engine* e, const std::string& k) {
+  auto it = e->raw.find(k);
+  if (it != e->raw.end()) { cudaFree(it->second.first); e->raw.erase(it); }
+}
+
+static int free_activations(pgibbs_engine* e) {
+  void* bufs[] = {e->tokens, e->x, e->h, e->qkv, e->ctx, e->ffn, e->hs, e->g, e->logits, e->scores, e->identity_pos};
+  for (void* b : bufs) if (b) cudaFree(b);
+  e->tokens = nullptr; e->x = nullptr; e->h = e->qkv = e->ctx = e->ffn = e->hs = nullptr;
+  e->g = e->logits = e->scores = nullptr; e->identity_pos = nullptr;
+  return 0;
+}
+
+static int build_weight_maps(pgibbs_engine* e) {
+  const int d = e->cfg.embed_dim, F = e->cfg.ffn_dim;
+  for (auto& l : e->L) {
+    TRY(make_tmap_2d(&l.m_wqkv, l.wqkv, 3 * d, d, d, e->bn_qkv));
+    TRY(make_tmap_2d(&l.m_wo, l.wo, d, d, d, e->bn_o));
+    TRY(make_tmap_2d(&l.m_w1, l.w1, F, d, d, e->bn_fc1));
+    TRY(make_tmap_2d(&l.m_w2, l.w2, d, F, F, e->bn_fc2));
+    if (e->cfg.arch == PGIBBS_ARCH_MSA) {
+      TRY(make_tmap_2d(&l.m_cwqkv, l.c_wqkv, 3 * d, d, d, e->bn_qkv));
+      TRY(make_tmap_2d(&l.m_cwo, l.c_wo, d, d, d, e->bn_o));
+    }
+  }
+  TRY(make_tmap_2d(&e->m_wdense, e->w_dense, d, d, d, e->bn_dense));
+  return 0;
+}
+
+static int ensure_shape(pgibbs_engine* e, int B, int R, int T) {
+  if (B <= 0 || R <= 0 || T <= 0) return fail("invalid token shape (%d,%d,%d)", B, R, T);
+  if (e->cfg.arch != PGIBBS_ARCH_MSA && R != 1) return fail("single-sequence model needs R == 1, got %d", R);
+  if (e->cfg.arch != PGIBBS_ARCH_ESM2 && T > e->cfg.max_positions)
+    return fail("sequence of %d tokens exceeds the learned position table (%d)", T, e->cfg.max_positions);
+  if (e->cfg.arch == PGIBBS_ARCH_MSA && R > 1024) return fail("MSA depth %d exceeds 1024", R);
+  if (B == e->B && R == e->R && T == e->T) return 0;
+  CK(cudaStreamSynchronize(e->stream));
+  free_activations(e);
+  const int d = e->cfg.embed_dim, F = e->cfg.ffn_dim, V = e->cfg.vocab;
+  e->B = B; e->R = R; e->T = T; e->n_seq = B * R;
+  const size_t M = static_cast<size_t>(B) * R * T;
+  e->M = static_cast<int>(M);
+  TRY(dev_alloc(&e->tokens, M));
+  TRY(dev_alloc(&e->x, M * d));
+  TRY(dev_alloc(&e->h, M * d));
+  TRY(dev_alloc(&e->qkv, M * 3 * d));
+  TRY(dev_alloc(&e->ctx, M * d));
+  TRY(dev_alloc(&e->ffn, M * F));
+  TRY(dev_alloc(&e->hs, M * d));
+  TRY(dev_alloc(&e->g, M * d));
+  TRY(dev_alloc(&e->logits, M * V));
+  if (e->cfg.arch == PGIBBS_ARCH_MSA)
+    TRY(dev_alloc(&e->scores, static_cast<size_t>(B) * e->cfg.heads * T * T));
+  TRY(dev_alloc(&e->identity_pos, static_cast<size_t>(T)));
+  std::vector<int32_t> idp(T);
+  for (int i = 0; i < T; ++i) idp[i] = i;
+  CK(cudaMemcpy(e->identity_pos, idp.data(), T * sizeof(int32_t), cudaMemcpyHostToDevice));
+  TRY(make_tmap_2d(&e->m_h, e->h, M, d, d, kBM));
+  TRY(make_tmap_2d(&e->m_ctx, e->ctx, M, d, d, kBM));
+  TRY(make_tmap_2d(&e->m_ffn, e->ffn, M, F, F, kBM));
+  TRY(make_tmap_2d(&e->m_hs, e->hs, M, d, d, kBM));
+  const int hd = d / e->cfg.heads;
+  e->bn_qkv = pick_block_n(e->M, 3 * d, hd >= 64 ? 64 : 32);
+  e->bn_o = pick_block_n(e->M, d, 16);
+  e->bn_fc1 = pick_block_n(e->M, F, 16);
+  e->bn_fc2 = pick_block_n(e->M, d, 16);
+  e->bn_dense = pick_block_n(e->M, d, 16);
+  TRY(build_weight_maps(e));
+  if (e->cfg.arch == PGIBBS_ARCH_ESM2 && e->rope_T < T) {
+    if (e->rope) cudaFree(e->rope);
+    TRY(dev_alloc(&e->rope, static_cast<size_t>(T) * (hd / 2)));
+    rope_table_kernel<<<(T * (hd / 2) + 255) / 256, 256, 0, e->stream>>>(e->rope, T, hd / 2);
+    CK(cudaGetLastError());
+    e->rope_T = T;
+  }
+  return 0;
+}
+
+// ----------------------------------------------------------------------------- the forward pass
+static int run_ln(pgibbs_engine* e, const float* x, const float* w, const float* b, __half* out, int rows,
+                  const Schedule* gather, int iter) {
+  LnParams p{};
+  p.x = x; p.w = w; p.b = b; p.out = out; p.rows_out = rows; p.d = e->cfg.embed_dim; p.eps = 1e-5f;
+  if (gather) p.sched = *gather; else p.sched.positions = nullptr;
+  p.iter = iter; p.T = e->T;
+  ProfScope ps(e, "layernorm");
+  layernorm_kernel<true><<<(rows + 7) / 8, 256, 0, e->stream>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int run_gemm(pgibbs_engine* e, const char* name, int epi, int bn, const CUtensorMap& a, const CUtensorMap& b,
+                    GemmParams p) {
+  ProfScope ps(e, name);
+  return launch_gemm(epi, bn, a, b, p, e->stream);
+}
+
+static int run_attention(pgibbs_engine* e) {
+  const int d = e->cfg.embed_dim, H = e->cfg.heads, hd = d / H;
+  AttnParams p{e->qkv, e->ctx, e->T, 3 * d, d, d, 2 * d};
+  dim3 grid((e->T + kAttnBQ - 1) / kAttnBQ, H, e->n_seq);
+  ProfScope ps(e, "attention");
+  switch (hd) {
+    case 16: attention_kernel<16><<<grid, 128, 0, e->stream>>>(p); break;
+    case 32: attention_kernel<32><<<grid, 128, 0, e->stream>>>(p); break;
+    case 64: attention_kernel<64><<<grid, 128, 0, e->stream>>>(p); break;
+    default: return fail("unsupported head_dim %d (16, 32, 64)", hd);
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static GemmParams gp(int M, int N, int K, const float* bias, void* out, int ldo) {
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.ldo = ldo;
+  return p;
+}
+
+// One transformer forward over the resident tokens.  `sched`: rows the LM head is evaluated on (chain-major);
+// sampling writes tokens when `sample` is set, logits rows are stored when `logits_out` is non-null.
+static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int iter, bool sample, int k_eff,
+                   float temperature, int n_valid, float* logits_out) {
+  const auto& c = e->cfg;
+  const int d = c.embed_dim, F = c.ffn_dim, M = e->M, hd = d / c.heads;
+  cudaStream_t st = e->stream;
+  {
+    EmbedParams p{};
+    p.tokens = e->tokens;
+    p.tok_emb = raw_get(e, "embed_tokens.weight", -1);
+    p.pos_emb = c.arch == PGIBBS_ARCH_ESM2 ? nullptr : raw_get(e, "embed_positions.weight", -1);
+    p.row_emb = c.arch == PGIBBS_ARCH_MSA ? raw_get(e, "msa_position_embedding", -1) : nullptr;
+    if (c.arch != PGIBBS_ARCH_ESM2) {
+      p.ln_w = raw_get(e, "emb_layer_norm_before.weight", -1);
+      p.ln_b = raw_get(e, "emb_layer_norm_before.bias", -1);
+    }
+    p.x = e->x; p.n_seq = e->n_seq; p.T = e->T; p.d = d; p.rows_per_msa = e->R;
+    p.mask_idx = c.mask_idx; p.token_dropout = c.token_dropout; p.eps = 1e-5f;
+    ProfScope ps(e, "embed");
+    embed_kernel<<<(M + 7) / 8, 256, 0, st>>>(p);
+    CK(cudaGetLastError());
+  }
+  const int n_layers = e->layer_limit >= 0 ? std::min(e->layer_limit, c.layers) : c.layers;
+  for (int li = 0; li < n_layers; ++li) {
+    LayerW& l = e->L[li];
+    if (c.arch == PGIBBS_ARCH_MSA) {
+      const float row_scale = (1.0f / sqrtf(static_cast<float>(hd))) / sqrtf(static_cast<float>(e->R));
+      // tied row attention
+      TRY(run_ln(e, e->x, l.ln1w, l.ln1b, e->h, M, nullptr, 0));
+      GemmParams q = gp(M, 3 * d, d, l.bqkv, e->qkv, 3 * d);
+      q.q_cols = d; q.q_scale = row_scale; q.rope_cols = 0; q.head_dim = hd; q.seq_len = e->T;
+      TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->bn_qkv, e->m_h, l.m_wqkv, q));
+      {
+        ProfScope ps(e, "msa_row_attention");
+        if (const char* m = launch_msa_row_attention(e->qkv, e->ctx, e->scores, e->B, e->R, e->T, c.heads, hd, st)) return fail("%s", m);
+      }
+      TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->bn_o, e->m_ctx, l.m_wo, gp(M, d, d, l.bo, e->x, d)));
+      // column attention
+      TRY(run_ln(e, e->x, l.lncw, l.lncb, e->h, M, nullptr, 0));
+      if (e->R == 1) return fail("MSA depth 1 is not supported by the column-attention kernel");
+      GemmParams qc = gp(M, 3 * d, d, l.c_bqkv, e->qkv, 3 * d);
+      qc.q_cols = d; qc.q_scale = 1.0f / sqrtf(static_cast<float>(hd)); qc.rope_cols = 0; qc.head_dim = hd;
+      qc.seq_len = e->T;
+      TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->bn_qkv, e->m_h, l.m_cwqkv, qc));
+      {
+        ProfScope ps(e, "msa_col_attention");
+        if (const char* m = launch_msa_col_attention(e->qkv, e->ctx, e->B, e->R, e->T, c.heads, hd, st)) return fail("%s", m);
+      }
+      TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->bn_o, e->m_ctx, l.m_cwo, gp(M, d, d, l.c_bo, e->x, d)));
+    } else {
+      TRY(run_ln(e, e->x, l.ln1w, l.ln1b, e->h, M, nullptr, 0));
+      GemmParams q = gp(M, 3 * d, d, l.bqkv, e->qkv, 3 * d);
+      q.q_cols = d; q.q_scale = 1.0f / sqrtf(static_cast<float>(hd));
+      q.rope_cols = c.arch == PGIBBS_ARCH_ESM2 ? 2 * d : 0;
+      q.head_dim = hd; q.seq_len = e->T; q.rope = e->rope;
+      TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->bn_qkv, e->m_h, l.m_wqkv, q));
+      TRY(run_attention(e));
+      TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->bn_o, e->m_ctx, l.m_wo, gp(M, d, d, l.bo, e->x, d)));
+    }
+    TRY(run_ln(e, e->x, l.ln2w, l.ln2b, e->h, M, nullptr, 0));
+    TRY(run_gemm(e, "gemm_fc1", EPI_GELU_F16, e->bn_fc1, e->m_h, l.m_w1, gp(M, F, d, l.b1, e->ffn, F)));
+    TRY(run_gemm(e, "gemm_fc2", EPI_RESID_F32, e->bn_fc2, e->m_ffn, l.m_w2, gp(M, d, F, l.b2, e->x, d)));
+  }
+  // LM head on the scheduled rows only
+  const int rows = n_chains * sched.P;
+  TRY(run_ln(e, e->x, raw_get(e, "emb_layer_norm_after.weight", -1), raw_get(e, "emb_layer_norm_after.bias", -1),
+             e->hs, rows, &sched, iter));
+  TRY(run_gemm(e, "gemm_head", EPI_GELU_F32, e->bn_dense, e->m_hs, e->m_wdense, gp(rows, d, d, e->b_dense, e->g, d)));
+  {
+    HeadParams p{};
+    p.g = e->g;
+    p.ln_w = raw_get(e, "lm_head.layer_norm.weight", -1);
+    p.ln_b = raw_get(e, "lm_head.layer_norm.bias", -1);
+    p.emb = raw_get(e, "embed_tokens.weight", -1);
+    p.out_bias = raw_get(e, "lm_head.bias", -1);
+    p.logits_out = logits_out;
+    p.tokens = sample ? e->tokens : nullptr;
+    p.rows = rows; p.d = d; p.V = c.vocab; p.T = e->T; p.eps = 1e-5f;
+    p.sched = sched; p.iter = iter;
+    p.valid_ids = e->valid_dev; p.n_valid = n_valid; p.top_k = k_eff; p.temperature = temperature;
+    p.noise = (sample && e->noise) ? e->noise + static_cast<int64_t>(iter) * rows * e->noise_stride : nullptr;
+    p.noise_stride = e->noise_stride;
+    p.seed = e->seed;
+    p.skip_dup_writes = e->has_dup;
+    const size_t emb_bytes = static_cast<size_t>(c.vocab) * d * sizeof(float);
+    p.emb_in_smem = emb_bytes <= 200 * 1024;
+    static bool configured = false;
+    if (!configured) {
+      CK(cudaFuncSetAttribute(head_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    const int grid = std::min(g_num_sms, (rows + 7) / 8);
+    ProfScope ps(e, "head_sample");
+    head_sample_kernel<<<grid, 256, p.emb_in_smem ? emb_bytes : 0, st>>>(p);
+    CK(cudaGetLastError());
+  }
+  return 0;
+}
+
+static int check_ready(pgibbs_engine* e) {
+  if (!e) return fail("null engine");
+  CK(cudaSetDevice(e->device));
+  if (!e->finalized) return fail("weights not finalized (call pgibbs_finalize_weights)");
+  return 0;
+}
+
+static int upload_valid(pgibbs_engine* e, const int32_t* valid_ids, int n_valid) {
+  if (n_valid <= 0 || n_valid > 32) return fail("n_valid=%d out of range (1..32)", n_valid);
+  std::vector<int32_t> v(n_valid);
+  CK(cudaMemcpy(v.data(), valid_ids, n_valid * sizeof(int32_t), cudaMemcpyDefault));
+  for (int i = 0; i < n_valid; ++i)
+    if (v[i] < 0 || v[i] >= e->cfg.vocab) return fail("valid id %d outside vocabulary", v[i]);
+  if (!e->valid_dev) TRY(dev_alloc(&e->valid_dev, 32));
+  CK(cudaMemcpyAsync(e->valid_dev, v.data(), n_valid * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));  // v is a stack-backed vector
+  return 0;
+}
+
+static int run_iters(pgibbs_engine* e, int first_iter, int num_iters, int64_t burnin, int top_k, float temperature,
+                     int mask_flag, int mask_row, int target_row, bool single, const int32_t* valid_ids,
+                     int n_valid) {
+  TRY(check_ready(e));
+  if (!e->tokens) return fail("no tokens resident (call pgibbs_set_tokens)");
+  if (!e->positions) return fail("no schedule set (call pgibbs_set_schedule)");
+  if (first_iter < 0 || first_iter + num_iters > e->n_iters)
+    return fail("iterations [%d,%d) outside the schedule (%d)", first_iter, first_iter + num_iters, e->n_iters);
+  TRY(upload_valid(e, valid_ids, n_valid));
+  const int n_chains = single ? e->B : e->n_seq;
+  const int64_t rows = static_cast<int64_t>(n_chains) * e->P;
+  if (static_cast<int64_t>(e->n_iters - 1) * e->iter_stride + static_cast<int64_t>(n_chains - 1) * e->chain_stride +
+          e->P > e->positions_used)
+    return fail("schedule buffer too small for %d chains", n_chains);
+  if (e->noise && e->noise_numel < static_cast<int64_t>(first_iter + num_iters) * rows * e->noise_stride)
+    return fail("replay noise too short for the requested iterations");
+  Schedule s{e->positions, e->iter_stride, e->chain_stride, e->P, single ? e->R : 1, single ? target_row : 0};
+  for (int it = first_iter; it < first_iter + num_iters; ++it) {
+    if (mask_flag) {
+      Schedule ms = s;
+      if (single) ms.seq_offset = mask_row;
+      ProfScope ps(e, "mask_scatter");
+      mask_scatter_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, e->stream>>>(
+          e->tokens, n_chains, e->T, ms, it, e->cfg.mask_idx);
+      CK(cudaGetLastError());
+    }
+    const int k_eff = (it < burnin || top_k <= 0 || top_k > n_valid) ? n_valid : top_k;
+    TRY(forward(e, s, n_chains, it, true, k_eff, temperature, n_valid, nullptr));
+  }
+  return 0;
+}
+
+}  // namespace pg
+
+// =========================================================================================== C ABI
+extern "C" {
+
+const char* pgibbs_last_error(void) { return g_err; }
+const char* pgibbs_version(void) { return "pgibbs 0.1 sm_100a (tcgen05/TMA GEMM, fp16 operands, fp32 accumulate)"; }
+
+int pgibbs_create(const pgibbs_model_config* cfg, int32_t device_id, pgibbs_engine** out) {
+  if (!cfg || !out) return fail("null argument");
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail("no CUDA device found");
+  if (device_id < 0 || device_id >= n_dev) return fail("invalid cuda device number: %d", device_id);
+  CK(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major != 10) return fail("device %d is sm_%d%d; this engine only runs on sm_100 (B200)", device_id, prop.major, prop.minor);
+  g_num_sms = prop.multiProcessorCount;
+  if (cfg->embed_dim % cfg->heads) return fail("embed_dim %% heads != 0");
+  if (cfg->embed_dim % 64 || cfg->ffn_dim % 64) return fail("embed_dim and ffn_dim must be multiples of 64");
+  if (cfg->embed_dim > kMaxVecPerLane * 128) return fail("embed_dim %d too large (max %d)", cfg->embed_dim, kMaxVecPerLane * 128);
+  if (cfg->vocab > 64) return fail("vocab %d too large (max 64)", cfg->vocab);
+  pgibbs_engine* e = new pgibbs_engine();
+  e->cfg = *cfg;
+  e->device = device_id;
+  if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete e;
+    return fail("cudaStreamCreate failed");
+  }
+  e->stream = e->own_stream;
+  *out = e;
+  return 0;
+}
+
+int pgibbs_destroy(pgibbs_engine* e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  free_activations(e);
+  for (auto& kv : e->raw) cudaFree(kv.second.first);
+  for (void* p : e->owned) cudaFree(p);
+  if (e->rope) cudaFree(e->rope);
+  if (e->positions) cudaFree(e->positions);
+  if (e->noise) cudaFree(e->noise);
+  if (e->valid_dev) cudaFree(e->valid_dev);
+  for (auto& t : e->prof_pending) { cudaEventDestroy(std::get<1>(t)); cudaEventDestroy(std::get<2>(t)); }
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+  return 0;
+}
+
+int pgibbs_set_stream(pgibbs_engine* e, void* cuda_stream) {
+  if (!e) return fail("null engine");
+  CK(cudaStreamSynchronize(e->stream));
+  e->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+  return 0;
+}
+
+int pgibbs_load_weight(pgibbs_engine* e, const char* name, const float* data, int64_t numel) {
+  if (!e || !name || !data || numel <= 0) return fail("invalid argument to pgibbs_load_weight");
+  CK(cudaSetDevice(e->device));
+  if (e->finalized) return fail("weights already finalized");
+  float* dptr = nullptr;
+  TRY(dev_alloc(&dptr, static_cast<size_t>(numel)));
+  if (cudaMemcpy(dptr, data, numel * sizeof(float), cudaMemcpyDefault) != cudaSuccess) {
+    cudaFree(dptr);
+    return fail("copy of weight '%s' failed", name);
+  }
+  auto it = e->raw.find(name);
+  if (it != e->raw.end()) cudaFree(it->second.first);
+  e->raw[name] = {dptr, numel};
+  return 0;
+}
+
+int pgibbs_finalize_weights(pgibbs_engine* e) {
+  if (!e) return fail("null engine");
+  CK(cudaSetDevice(e->device));
+  if (e->finalized) return 0;
+  const auto& c = e->cfg;
+  const int64_t d = c.embed_dim, F = c.ffn_dim, V = c.vocab;
+  if (!raw_get(e, "embed_tokens.weight", V * d)) return 1;
+  if (c.arch != PGIBBS_ARCH_ESM2) {
+    if (!raw_get(e, "embed_positions.weight", (c.max_positions + 2) * d)) return 1;
+    if (!raw_get(e, "emb_layer_norm_before.weight", d) || !raw_get(e, "emb_layer_norm_before.bias", d)) return 1;
+  }
+  if (c.arch == PGIBBS_ARCH_MSA && !raw_get(e, "msa_position_embedding", 1024 * d)) return 1;
+  if (!raw_get(e, "emb_layer_norm_after.weight", d) || !raw_get(e, "emb_layer_norm_after.bias", d)) return 1;
+  if (!raw_get(e, "lm_head.layer_norm.weight", d) || !raw_get(e, "lm_head.layer_norm.bias", d)) return 1;
+  if (!raw_get(e, "lm_head.bias", V)) return 1;
+  e->L.resize(c.layers);
+  for (int i = 0; i < c.layers; ++i) {
+    LayerW& l = e->L[i];
+    const std::string p = "layers." + std::to_string(i) + ".";
+    std::string attn, ln1, ffn, ln2;
+    if (c.arch == PGIBBS_ARCH_MSA) {
+      attn = p + "row_self_attention.layer."; ln1 = p + "row_self_attention.layer_norm";
+      ffn = p + "feed_forward_layer.layer."; ln2 = p + "feed_forward_layer.layer_norm";
+    } else {
+      attn = p + "self_attn."; ln1 = p + "self_attn_layer_norm"; ffn = p; ln2 = p + "final_layer_norm";
+    }
+    TRY(pack_qkv(e, attn, &l.wqkv, &l.bqkv));
+    TRY(pack_linear(e, attn + "out_proj", d, d, &l.wo, &l.bo));
+    TRY(pack_linear(e, ffn + "fc1", F, d, &l.w1, &l.b1));
+    TRY(pack_linear(e, ffn + "fc2", d, F, &l.w2, &l.b2));
+    if (!(l.ln1w = raw_get(e, ln1 + ".weight", d)) || !(l.ln1b = raw_get(e, ln1 + ".bias", d))) return 1;
+    if (!(l.ln2w = raw_get(e, ln2 + ".weight", d)) || !(l.ln2b = raw_get(e, ln2 + ".bias", d))) return 1;
+    if (c.arch == PGIBBS_ARCH_MSA) {
+      const std::string ca = p + "column_self_attention.layer.", cl = p + "column_self_attention.layer_norm";
+      TRY(pack_qkv(e, ca, &l.c_wqkv, &l.c_bqkv));
+      TRY(pack_linear(e, ca + "out_proj", d, d, &l.c_wo, &l.c_bo));
+      if (!(l.lncw = raw_get(e, cl + ".weight", d)) || !(l.lncb = raw_get(e, cl + ".bias", d))) return 1;
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    // the fp32 copies of GEMM weights are no longer needed (biases / LN params stay)
+    for (const char* nm : {"q_proj", "k_proj", "v_proj", "out_proj"}) {
+      drop_raw(e, attn + nm + ".weight");
+      if (c.arch == PGIBBS_ARCH_MSA) drop_raw(e, p + "column_self_attention.layer." + nm + ".weight");
+    }
+    drop_raw(e, ffn + "fc1.weight");
+    drop_raw(e, ffn + "fc2.weight");
+  }
+  TRY(pack_linear(e, "lm_head.dense", d, d, &e->w_dense, &e->b_dense));
+  CK(cudaStreamSynchronize(e->stream));
+  drop_raw(e, "lm_head.dense.weight");
+  e->finalized = true;
+  return 0;
+}
+
+int pgibbs_set_tokens(pgibbs_engine* e, const int32_t* tokens, int32_t B, int32_t R, int32_t T) {
+  TRY(check_ready(e));
+  if (!tokens) return fail("null tokens");
+  const size_t n = static_cast<size_t>(B) * R * T;
+  std::vector<int32_t> host(n);
+  CK(cudaMemcpy(host.data(), tokens, n * sizeof(int32_t), cudaMemcpyDefault));
+  for (size_t i = 0; i < n; ++i) {
+    if (host[i] < 0 || host[i] >= e->cfg.vocab) return fail("token id %d at %zu outside vocabulary", host[i], i);
+    if (host[i] == e->cfg.padding_idx)
+      return fail("<pad> token at flat index %zu: padded batches are not on the Gibbs path and are not supported", i);
+  }
+  TRY(ensure_shape(e, B, R, T));
+  CK(cudaMemcpyAsync(e->tokens, host.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+int pgibbs_get_tokens(pgibbs_engine* e, int32_t* tokens_out) {
+  TRY(check_ready(e));
+  if (!e->tokens || !tokens_out) return fail("no tokens resident or null output");
+  CK(cudaMemcpyAsync(tokens_out, e->tokens, static_cast<size_t>(e->M) * sizeof(int32_t), cudaMemcpyDefault, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  TRY(prof_flush(e));
+  return 0;
+}
+
+int pgibbs_set_schedule(pgibbs_engine* e, const int32_t* positions, int64_t numel, int32_t n_iters, int32_t P,
+                        int64_t iter_stride, int64_t chain_stride, int32_t has_duplicates) {
+  TRY(check_ready(e));
+  if (!e->tokens) return fail("set tokens before the schedule");
+  if (!positions || numel <= 0 || n_iters <= 0 || P <= 0) return fail("invalid schedule");
+  if (P > e->T) return fail("P=%d exceeds the sequence length %d", P, e->T);
+  if (chain_stride < 0 || iter_stride < 0) return fail("negative schedule stride");
+  if (static_cast<int64_t>(n_iters - 1) * iter_stride + P > numel) return fail("schedule buffer too small");
+  std::vector<int32_t> host(numel);
+  CK(cudaMemcpy(host.data(), positions, numel * sizeof(int32_t), cudaMemcpyDefault));
+  for (int64_t i = 0; i < numel; ++i)
+    if (host[i] < 0 || host[i] >= e->T) return fail("scheduled position %d outside [0,%d)", host[i], e->T);
+  CK(cudaStreamSynchronize(e->stream));
+  if (e->positions_numel < numel) {
+    if (e->positions) cudaFree(e->positions);
+    TRY(dev_alloc(&e->positions, static_cast<size_t>(numel)));
+    e->positions_numel = numel;
+  }
+  CK(cudaMemcpy(e->positions, host.data(), numel * sizeof(int32_t), cudaMemcpyHostToDevice));
+  e->positions_used = numel;
+  e->n_iters = n_iters; e->P = P; e->iter_stride = iter_stride; e->chain_stride = chain_stride;
+  e->has_dup = has_duplicates;
+  return 0;
+}
+
+int pgibbs_set_noise(pgibbs_engine* e, const float* exp_noise, int64_t numel, int32_t stride) {
+  TRY(check_ready(e));
+  CK(cudaStreamSynchronize(e->stream));
+  if (e->noise) { cudaFree(e->noise); e->noise = nullptr; e->noise_numel = 0; }
+  if (!exp_noise || numel <= 0) return 0;
+  if (stride <= 0 || stride > 32) return fail("noise stride %d out of range", stride);
+  TRY(dev_alloc(&e->noise, static_cast<size_t>(numel)));
+  CK(cudaMemcpy(e->noise, exp_noise, numel * sizeof(float), cudaMemcpyDefault));
+  e->noise_numel = numel;
+  e->noise_stride = stride;
+  return 0;
+}
+
+int pgibbs_set_device_rng(pgibbs_engine* e, uint64_t seed) {
+  if (!e) return fail("null engine");
+  e->seed = seed;
+  return 0;
+}
+
+int pgibbs_run(pgibbs_engine* e, int32_t first_iter, int32_t num_iters, int64_t burnin, int32_t top_k,
+               float temperature, int32_t mask_flag, const int32_t* valid_ids, int32_t n_valid) {
+  return run_iters(e, first_iter, num_iters, burnin, top_k, temperature, mask_flag, 0, 0, false, valid_ids, n_valid);
+}
+
+int pgibbs_run_single(pgibbs_engine* e, int32_t first_iter, int32_t num_iters, int64_t burnin, int32_t top_k,
+                      float temperature, int32_t mask_row, int32_t target_row, const int32_t* valid_ids,
+                      int32_t n_valid) {
+  if (!e) return fail("null engine");
+  if (e->cfg.arch != PGIBBS_ARCH_MSA) return fail("pgibbs_run_single needs an MSA model");
+  if (mask_row < 0) mask_row += e->R;
+  if (target_row < 0) target_row += e->R;
+  if (mask_row < 0 || mask_row >= e->R || target_row < 0 || target_row >= e->R) return fail("row index out of range");
+  return run_iters(e, first_iter, num_iters, burnin, top_k, temperature, 1, mask_row, target_row, true, valid_ids,
+                   n_valid);
+}
+
+int pgibbs_forward_logits(pgibbs_engine* e, const int32_t* tokens, int32_t B, int32_t R, int32_t T,
+                          float* logits_out) {
+  TRY(pgibbs_set_tokens(e, tokens, B, R, T));
+  if (!logits_out) return fail("null logits_out");
+  Schedule s{e->identity_pos, 0, 0, T, 1, 0};
+  TRY(forward(e, s, e->n_seq, 0, false, 0, -1.f, 0, e->logits));
+  CK(cudaMemcpyAsync(logits_out, e->logits, static_cast<size_t>(e->M) * e->cfg.vocab * sizeof(float),
+                     cudaMemcpyDefault, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  TRY(prof_flush(e));
+  return 0;
+}
+
+int pgibbs_sync(pgibbs_engine* e) {
+  if (!e) return fail("null engine");
+  CK(cudaSetDevice(e->device));
+  CK(cudaStreamSynchronize(e->stream));
+  TRY(prof_flush(e));
+  return 0;
+}
+
+int pgibbs_debug_read(pgibbs_engine* e, const char* which, float* out, int64_t numel) {
+  TRY(check_ready(e));
+  CK(cudaStreamSynchronize(e->stream));
+  const int64_t M = e->M, d = e->cfg.embed_dim, F = e->cfg.ffn_dim;
+  const std::string w = which ? which : "";
+  const __half* src16 = nullptr;
+  const float* src32 = nullptr;
+  int64_t n = 0;
+  if (w == "x") { src32 = e->x; n = M * d; }
+  else if (w == "g") { src32 = e->g; n = M * d; }
+  else if (w == "h") { src16 = e->h; n = M * d; }
+  else if (w == "hs") { src16 = e->hs; n = M * d; }
+  else if (w == "qkv") { src16 = e->qkv; n = M * 3 * d; }
+  else if (w == "ctx") { src16 = e->ctx; n = M * d; }
+  else if (w == "ffn") { src16 = e->ffn; n = M * F; }
+  else return fail("unknown debug buffer '%s'", w.c_str());
+  if (numel > n) numel = n;
+  if (src32) {
+    CK(cudaMemcpy(out, src32, numel * sizeof(float), cudaMemcpyDefault));
+  } else {
+    float* tmp = nullptr;
+    TRY(dev_alloc(&tmp, static_cast<size_t>(numel)));
+    f16_to_f32_kernel<<<static_cast<unsigned>((numel + 255) / 256), 256, 0, e->stream>>>(src16, tmp, numel);
+    cudaError_t er = cudaStreamSynchronize(e->stream);
+    if (er == cudaSuccess) er = cudaMemcpy(out, tmp, numel * sizeof(float), cudaMemcpyDefault);
+    cudaFree(tmp);
+    if (er != cudaSuccess) return fail("debug read failed: %s", cudaGetErrorString(er));
+  }
+  return 0;
+}
+
+int pgibbs_debug_layer_limit(pgibbs_engine* e, int32_t n_layers) {
+  if (!e) return fail("null engine");
+  e->layer_limit = n_layers;
+  return 0;
+}
+
+int pgibbs_profile_enable(pgibbs_engine* e, int32_t on) {
+  if (!e) return fail("null engine");
+  TRY(prof_flush(e));
+  e->prof = on != 0;
+  if (on) e->prof_acc.clear();
+  return 0;
+}
+
+int pgibbs_profile_read(pgibbs_engine* e, char (*names)[32], float* total_ms, int32_t* launches, int32_t cap,
+                        int32_t* n) {
+  if (!e || !n) return fail("null argument");
+  TRY(prof_flush(e));
+  int i = 0;
+  for (auto& kv : e->prof_acc) {
+    if (i >= cap) break;
+    snprintf(names[i], 32, "%s", kv.first.c_str());
+    total_ms[i] = static_cast<float>(kv.second.ms);
+    launches[i] = kv.second.launches;
+    ++i;
+  }
+  *n = i;
+  return 0;
+}
+
+int64_t pgibbs_launch_count(pgibbs_engine* e) { return e ? e->launches : 0; }
+
+// ------------------------------------------------------------------------ stand-alone operator entry points
+static int op_device(int device_id) {
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) return fail("no CUDA device found");
+  if (device_id < 0 || device_id >= n_dev) return fail("invalid cuda device number: %d", device_id);
+  CK(cudaSetDevice(device_id));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device_id));
+  if (prop.major != 10) return fail("device %d is not sm_100", device_id);
+  g_num_sms = prop.multiProcessorCount;
+  return 0;
+}
+
+int pgibbs_op_gemm(int32_t device_id, const float* A, const float* B, const float* bias, float* C, int32_t M,
+                   int32_t N, int32_t K, int32_t epilogue, int32_t block_n, float* elapsed_ms, int32_t reps) {
+  TRY(op_device(device_id));
+  if (epilogue == EPI_QKV_F16) return fail("use the engine for the QKV epilogue");
+  const size_t na = static_cast<size_t>(M) * K, nb = static_cast<size_t>(N) * K, nc = static_cast<size_t>(M) * N;
+  float *dA = nullptr, *dB = nullptr, *dbias = nullptr, *dC32 = nullptr;
+  __half *hA = nullptr, *hB = nullptr, *dC16 = nullptr;
+  int rc = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  auto body = [&]() -> int {
+    TRY(dev_alloc(&dA, na)); TRY(dev_alloc(&dB, nb)); TRY(dev_alloc(&hA, na)); TRY(dev_alloc(&hB, nb));
+    TRY(dev_alloc(&dC32, nc)); TRY(dev_alloc(&dC16, nc));
+    CK(cudaMemcpy(dA, A, na * sizeof(float), cudaMemcpyDefault));
+    CK(cudaMemcpy(dB, B, nb * sizeof(float), cudaMemcpyDefault));
+    if (bias) { TRY(dev_alloc(&dbias, static_cast<size_t>(N))); CK(cudaMemcpy(dbias, bias, N * sizeof(float), cudaMemcpyDefault)); }
+    CK(cudaStreamCreate(&st));
+    TRY(to_f16(dA, hA, na, st)); TRY(to_f16(dB, hB, nb, st));
+    const bool out16 = epilogue == EPI_BIAS_F16 || epilogue == EPI_GELU_F16;
+    if (epilogue == EPI_RESID_F32) CK(cudaMemcpyAsync(dC32, C, nc * sizeof(float), cudaMemcpyDefault, st));
+    const int bn = block_n > 0 ? block_n : pick_block_n(M, N, 16);
+    CUtensorMap ma, mb;
+    TRY(make_tmap_2d(&ma, hA, M, K, K, kBM));
+    TRY(make_tmap_2d(&mb, hB, N, K, K, bn));
+    GemmParams p = gp(M, N, K, dbias, out16 ? static_cast<void*>(dC16) : static_cast<void*>(dC32), N);
+    TRY(launch_gemm(epilogue, bn, ma, mb, p, st));
+    CK(cudaStreamSynchronize(st));
+    if (out16) {
+      f16_to_f32_kernel<<<static_cast<unsigned>((nc + 255) / 256), 256, 0, st>>>(dC16, dC32, nc);
+      CK(cudaGetLastError());
+    }
+    CK(cudaMemcpyAsync(C, dC32, nc * sizeof(float), cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    if (elapsed_ms && reps > 0) {
+      CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      for (int i = 0; i < 3; ++i) TRY(launch_gemm(epilogue, bn, ma, mb, p, st));
+      CK(cudaEventRecord(e0, st));
+      for (int i = 0; i < reps; ++i) TRY(launch_gemm(epilogue, bn, ma, mb, p, st));
+      CK(cudaEventRecord(e1, st));
+      CK(cudaStreamSynchronize(st));
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      *elapsed_ms = ms / reps;
+    }
+    return 0;
+  };
+  rc = body();
+  for (void* p : {static_cast<void*>(dA), static_cast<void*>(dB), static_cast<void*>(dbias), static_cast<void*>(dC32),
+                  static_cast<void*>(hA), static_cast<void*>(hB), static_cast<void*>(dC16)})
+    if (p) cudaFree(p);
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (st) cudaStreamDestroy(st);
+  return rc;
+}
+
+int pgibbs_op_attention(int32_t device_id, const float* qkv, float* ctx, int32_t n_seq, int32_t T, int32_t heads,
+                        int32_t head_dim) {
+  TRY(op_device(device_id));
+  const int d = heads * head_dim;
+  const size_t nq = static_cast<size_t>(n_seq) * T * 3 * d, nc = static_cast<size_t>(n_seq) * T * d;
+  float *d32 = nullptr, *c32 = nullptr;
+  __half *d16 = nullptr, *c16 = nullptr;
+  auto body = [&]() -> int {
+    TRY(dev_alloc(&d32, nq)); TRY(dev_alloc(&d16, nq)); TRY(dev_alloc(&c32, nc)); TRY(dev_alloc(&c16, nc));
+    CK(cudaMemcpy(d32, qkv, nq * sizeof(float), cudaMemcpyDefault));
+    TRY(to_f16(d32, d16, nq, nullptr));
+    AttnParams p{d16, c16, T, 3 * d, d, d, 2 * d};
+    dim3 grid((T + kAttnBQ - 1) / kAttnBQ, heads, n_seq);
+    switch (head_dim) {
+      case 16: attention_kernel<16><<<grid, 128>>>(p); break;
+      case 32: attention_kernel<32><<<grid, 128>>>(p); break;
+      case 64: attention_kernel<64><<<grid, 128>>>(p); break;
+      default: return fail("unsupported head_dim %d", head_dim);
+    }
+    CK(cudaGetLastError());
+    f16_to_f32_kernel<<<static_cast<unsigned>((nc + 255) / 256), 256>>>(c16, c32, nc);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(ctx, c32, nc * sizeof(float), cudaMemcpyDefault));
+    return 0;
+  };
+  const int rc = body();
+  for (void* p : {static_cast<void*>(d32), static_cast<void*>(c32), static_cast<void*>(d16), static_cast<void*>(c16)})
+    if (p) cudaFree(p);
+  return rc;
+}
+
+int pgibbs_op_sample(int32_t device_id, const float* logits, const float* noise, int32_t rows, int32_t vocab,
+                     const int32_t* valid_ids, int32_t n_valid, int32_t top_k, float temperature,
+                     int32_t* tokens_out) {
+  TRY(op_device(device_id));
+  if (vocab > 64 || n_valid > 32 || n_valid <= 0) return fail("vocab <= 64 and 0 < n_valid <= 32 required");
+  float *dl = nullptr, *dn = nullptr;
+  int32_t *dv = nullptr, *dout = nullptr;
+  auto body = [&]() -> int {
+    TRY(dev_alloc(&dl, static_cast<size_t>(rows) * vocab));
+    TRY(dev_alloc(&dv, static_cast<size_t>(n_valid)));
+    TRY(dev_alloc(&dout, static_cast<size_t>(rows)));
+    CK(cudaMemcpy(dl, logits, static_cast<size_t>(rows) * vocab * sizeof(float), cudaMemcpyDefault));
+    CK(cudaMemcpy(dv, valid_ids, n_valid * sizeof(int32_t), cudaMemcpyDefault));
+    if (noise) {
+      TRY(dev_alloc(&dn, static_cast<size_t>(rows) * n_valid));
+      CK(cudaMemcpy(dn, noise, static_cast<size_t>(rows) * n_valid * sizeof(float), cudaMemcpyDefault));
+    }
+    const int k = (top_k <= 0 || top_k > n_valid) ? n_valid : top_k;
+    sample_rows_kernel<<<(rows + 7) / 8, 256>>>(dl, rows, vocab, dv, n_valid, k, temperature, dn, n_valid, 1234ull, dout);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(tokens_out, dout, rows * sizeof(int32_t), cudaMemcpyDefault));
+    return 0;
+  };
+  const int rc = body();
+  for (void* p : {static_cast<void*>(dl), static_cast<void*>(dn), static_cast<void*>(dv), static_cast<void*>(dout)})
+    if (p) cudaFree(p);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,432 @@
+// HBM-bound row-wise kernels of the Gibbs step: <mask> scatter, embedding prologue (token-dropout
+// rescale + learned positions + LayerNorm-before), LayerNorm (fp32 residual stream -> fp16 GEMM operand),
+// and the fused LM-head tail (LayerNorm + tied-embedding projection + top-k / categorical draw + write-back).
+// One warp per row everywhere; rows are 128-bit vectorised.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pg {
+
+constexpr int kMaxVecPerLane = 20;  // float4 per lane -> embed_dim <= 2560
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Position schedule view: positions[iter*iter_stride + chain*chain_stride + p], p < P.
+// "all positions" and in-order schedules share one list (strides 0).
+// Chain c owns token row  c*seq_stride + seq_offset  (1/0 normally; R/target_row for generate_single).
+struct Schedule {
+  const int32_t* positions;
+  long long iter_stride, chain_stride;
+  int P;
+  int seq_stride, seq_offset;
+};
+
+// ---------------------------------------------------------------------------------------------
+// <mask> scatter: tokens[chain][pos] = mask_idx for every scheduled position.
+// Reference: ESM_sampler.mask_target_indexes (esm_sampler.py:259-262), MSA variant esm_msa_sampler.py:255-259.
+// ---------------------------------------------------------------------------------------------
+__global__ void mask_scatter_kernel(int32_t* __restrict__ tokens, int n_chains, int T, Schedule s, int iter,
+                                    int mask_idx) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= static_cast<long long>(n_chains) * s.P) return;
+  const int chain = static_cast<int>(i / s.P), p = static_cast<int>(i % s.P);
+  const int pos = s.positions[iter * s.iter_stride + chain * s.chain_stride + p];
+  tokens[(static_cast<long long>(chain) * s.seq_stride + s.seq_offset) * T + pos] = mask_idx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Embedding prologue.  One warp per token row.
+//   ESM-1b/ESM-2 (fair-esm ProteinBertModel / ESM2):
+//       x = E[tok] (0 for <mask>) * 0.88 / (1 - n_mask/T)   [token_dropout]
+//       x += P[t + 2]   then LayerNorm_before                [learned positions, ESM-1b]
+//   MSA Transformer (App. A.4): x = E[tok] + P[c + 2] + P_row[r]; LayerNorm_before.  No token dropout.
+// No <pad> appears on the Gibbs path; the host rejects padded inputs.
+// ---------------------------------------------------------------------------------------------
+struct EmbedParams {
+  const int32_t* tokens;   // [n_seq, T]
+  const float* tok_emb;    // [V, d]
+  const float* pos_emb;    // [max_pos + 2, d] or nullptr
+  const float* row_emb;    // [1024, d] (MSA) or nullptr
+  const float* ln_w;       // LayerNorm-before (nullptr = none)
+  const float* ln_b;
+  float* x;                // [n_seq*T, d]
+  int n_seq, T, d, rows_per_msa;
+  int mask_idx, token_dropout;
+  float eps;
+};
+
+__global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= p.n_seq * p.T) return;
+  const int seq = row / p.T, t = row % p.T;
+  const int32_t* toks = p.tokens + static_cast<long long>(seq) * p.T;
+  const int tok = toks[t];
+  float den = 1.0f;
+  if (p.token_dropout) {
+    int n_mask = 0;
+    for (int i = lane; i < p.T; i += 32) n_mask += (toks[i] == p.mask_idx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) n_mask += __shfl_xor_sync(0xffffffffu, n_mask, o);
+    // mask_ratio_observed = n_mask / src_length; no <pad> on this path so src_length == T
+    den = 1.0f - __fdiv_rn(static_cast<float>(n_mask), static_cast<float>(p.T));
+  }
+  const bool zero = p.token_dropout && tok == p.mask_idx;
+  const float4* e = reinterpret_cast<const float4*>(p.tok_emb + static_cast<long long>(tok) * p.d);
+  const float4* pe = p.pos_emb ? reinterpret_cast<const float4*>(p.pos_emb + static_cast<long long>(t + 2) * p.d)
+                               : nullptr;
+  const float4* re = p.row_emb ? reinterpret_cast<const float4*>(
+                                     p.row_emb + static_cast<long long>(seq % p.rows_per_msa) * p.d)
+                               : nullptr;
+  const int nvec = p.d >> 2;
+  float4 v[kMaxVecPerLane];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxVecPerLane; ++k) {
+    const int i = lane + k * 32;
+    if (i < nvec) {
+      float4 a = zero ? make_float4(0, 0, 0, 0) : __ldg(e + i);
+      if (p.token_dropout) {
+        // x * (1 - 0.15*0.8) / (1 - ratio): multiply then divide, in fair-esm's order
+        const float num = 0.88f;
+        a.x = __fdiv_rn(a.x * num, den); a.y = __fdiv_rn(a.y * num, den);
+        a.z = __fdiv_rn(a.z * num, den); a.w = __fdiv_rn(a.w * num, den);
+      }
+      if (pe) { const float4 b = __ldg(pe + i); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+      if (re) { const float4 b = __ldg(re + i); a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+      v[k] = a;
+      sum += a.x + a.y + a.z + a.w;
+    }
+  }
+  float4* out = reinterpret_cast<float4*>(p.x + static_cast<long long>(row) * p.d);
+  if (p.ln_w) {
+    const float mean = warp_sum(sum) / p.d;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLane; ++k) {
+      const int i = lane + k * 32;
+      if (i < nvec) {
+        const float4 a = v[k];
+        sq += (a.x - mean) * (a.x - mean) + (a.y - mean) * (a.y - mean) + (a.z - mean) * (a.z - mean) +
+              (a.w - mean) * (a.w - mean);
+      }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / p.d + p.eps);
+    const float4* w = reinterpret_cast<const float4*>(p.ln_w);
+    const float4* b = reinterpret_cast<const float4*>(p.ln_b);
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLane; ++k) {
+      const int i = lane + k * 32;
+      if (i < nvec) {
+        const float4 a = v[k], g = __ldg(w + i), h = __ldg(b + i);
+        out[i] = make_float4((a.x - mean) * rstd * g.x + h.x, (a.y - mean) * rstd * g.y + h.y,
+                             (a.z - mean) * rstd * g.z + h.z, (a.w - mean) * rstd * g.w + h.w);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLane; ++k) {
+      const int i = lane + k * 32;
+      if (i < nvec) out[i] = v[k];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm over rows of the fp32 residual stream -> fp16 (GEMM A operand) or fp32.
+// Optional gather: output row i reads source row  chain*T + positions[...]  (LM head on sampled rows only).
+// ---------------------------------------------------------------------------------------------
+struct LnParams {
+  const float* x;  // [rows_src, d]
+  const float* w;
+  const float* b;
+  void* out;       // [rows_out, d] fp16 or fp32
+  int rows_out, d;
+  float eps;
+  // gather (positions == nullptr -> identity)
+  Schedule sched;
+  int iter, T;
+};
+
+template <bool OUT_F16>
+__global__ void __launch_bounds__(256) layernorm_kernel(LnParams p) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int orow = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (orow >= p.rows_out) return;
+  long long srow = orow;
+  if (p.sched.positions) {
+    const int chain = orow / p.sched.P, q = orow % p.sched.P;
+    srow = (static_cast<long long>(chain) * p.sched.seq_stride + p.sched.seq_offset) * p.T +
+           p.sched.positions[p.iter * p.sched.iter_stride + chain * p.sched.chain_stride + q];
+  }
+  const float4* in = reinterpret_cast<const float4*>(p.x + srow * p.d);
+  const int nvec = p.d >> 2;
+  float4 v[kMaxVecPerLane];
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxVecPerLane; ++k) {
+    const int i = lane + k * 32;
+    if (i < nvec) {
+      v[k] = in[i];
+      sum += v[k].x + v[k].y + v[k].z + v[k].w;
+    }
+  }
+  const float mean = warp_sum(sum) / p.d;
+  float sq = 0.f;
+#pragma unroll
+  for (int k = 0; k < kMaxVecPerLane; ++k) {
+    const int i = lane + k * 32;
+    if (i < nvec) {
+      const float4 a = v[k];
+      sq += (a.x - mean) * (a.x - mean) + (a.y - mean) * (a.y - mean) + (a.z - mean) * (a.z - mean) +
+            (a.w - mean) * (a.w - mean);
+    }
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(sq) / p.d + p.eps);
+  const float4* w = reinterpret_cast<const float4*>(p.w);
+  const float4* b = reinterpret_cast<const float4*>(p.b);
+#pragma unroll
+  for (int k = 0; k < kMaxVecPerLane; ++k) {
+    const int i = lane + k * 32;
+    if (i < nvec) {
+      const float4 a = v[k], g = __ldg(w + i), h = __ldg(b + i);
+      const float y0 = (a.x - mean) * rstd * g.x + h.x, y1 = (a.y - mean) * rstd * g.y + h.y;
+      const float y2 = (a.z - mean) * rstd * g.z + h.z, y3 = (a.w - mean) * rstd * g.w + h.w;
+      if constexpr (OUT_F16) {
+        __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+        uint2 u = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + static_cast<long long>(orow) * p.d)[i] = u;
+      } else {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(orow) * p.d)[i] =
+            make_float4(y0, y1, y2, y3);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Counter-based device RNG (Philox4x32-10) for the exponential race when no replay noise is supplied.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// generate_step (reference esm_sampler.py:8-45) for one row, executed by one warp.
+// `mine`/`extra`: lane v holds logit v (v < 32) / logit v+32.  Returns the sampled token id (all lanes).
+//   l = logits / temperature ; sub = l[valid_idx] ; (vals, idx) = topk(sub, k)
+//   Categorical(logits=vals).sample() == argmax_j softmax(vals - logsumexp(vals))_j / q_j,  q ~ Exp(1)
+//   (torch.multinomial's n_sample == 1 path); noise slot j pairs with the j-th largest candidate.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int generate_step_warp(float mine, float extra, int lane, int row, int iter,
+                                                  const int32_t* __restrict__ valid_ids, int n, int k,
+                                                  float temperature, const float* __restrict__ noise,
+                                                  int noise_stride, unsigned long long seed) {
+  const int my_id = lane < n ? valid_ids[lane] : 0;
+  float l = __shfl_sync(0xffffffffu, mine, my_id & 31);
+  const float l_hi = __shfl_sync(0xffffffffu, extra, my_id & 31);
+  if (my_id >= 32) l = l_hi;
+  if (temperature > 0.f) l = __fdiv_rn(l, temperature);
+  if (lane >= n) l = -INFINITY;
+  // rank = position in the descending top-k order (ties: lower candidate slot first)
+  int rank = 0;
+  for (int j = 0; j < n; ++j) {
+    const float o = __shfl_sync(0xffffffffu, l, j);
+    rank += (o > l) || (o == l && j < lane);
+  }
+  const bool in_top = lane < n && rank < k;
+  // Categorical.__init__: logits - logsumexp(logits); .probs = softmax(that)
+  float mx = in_top ? l : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float ex = in_top ? expf(l - mx) : 0.f;
+  const float lse = logf(warp_sum(ex)) + mx;
+  const float ln = l - lse;                       // normalised logits
+  float mx2 = in_top ? ln : -INFINITY;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx2 = fmaxf(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
+  const float ex2 = in_top ? expf(ln - mx2) : 0.f;
+  const float prob = __fdiv_rn(ex2, warp_sum(ex2));
+  float q = 1.f;
+  if (in_top) {
+    if (noise) {
+      q = noise[static_cast<long long>(row) * noise_stride + rank];
+    } else {
+      const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(iter), static_cast<uint32_t>(row),
+                                               static_cast<uint32_t>(rank), 0x5eedu),
+                                    make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+      const float u = (static_cast<float>(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+      q = -logf(u);
+    }
+  }
+  float score = in_top ? __fdiv_rn(prob, q) : -INFINITY;
+  // argmax over slots; ties -> lowest rank (torch.argmax returns the first maximum)
+  int best_rank = in_top ? rank : 0x7fffffff;
+  int best_id = my_id;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float os = __shfl_xor_sync(0xffffffffu, score, o);
+    const int orank = __shfl_xor_sync(0xffffffffu, best_rank, o);
+    const int oid = __shfl_xor_sync(0xffffffffu, best_id, o);
+    if (os > score || (os == score && orank < best_rank)) { score = os; best_rank = orank; best_id = oid; }
+  }
+  return best_id;
+}
+
+// generate_step on precomputed logits rows (operator-level parity tests of the sampler tail).
+__global__ void __launch_bounds__(256) sample_rows_kernel(const float* __restrict__ logits, int rows, int V,
+                                                          const int32_t* __restrict__ valid_ids, int n, int k,
+                                                          float temperature, const float* __restrict__ noise,
+                                                          int noise_stride, unsigned long long seed,
+                                                          int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* lr = logits + static_cast<long long>(row) * V;
+  const float mine = lane < V ? lr[lane] : 0.f;
+  const float extra = lane + 32 < V ? lr[lane + 32] : 0.f;
+  const int id = generate_step_warp(mine, extra, lane, row, 0, valid_ids, n, k, temperature, noise, noise_stride, seed);
+  if (lane == 0) out[row] = id;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused LM-head tail.  One warp per sampled row i (compact order: chain-major, then position slot):
+//   y = LayerNorm(g[i])                      (RobertaLMHead.layer_norm, fp32)
+//   logits[v] = <y, E[v]> + b[v], v < V      (tied embedding projection, fp32 on CUDA cores; V = 33)
+//   generate_step (reference esm_sampler.py:8-45):
+//       l = logits / temperature ; sub = l[valid_idx] ; k = (sample || top_k<=0 || top_k>n) ? n : top_k
+//       (vals, idx) = topk(sub, k) ; draw ~ Categorical(logits=vals) == argmax_j softmax(vals)_j / q_j, q~Exp(1)
+//       token = valid_idx[idx[draw]]
+//   tokens[chain][pos] = token                (write-back, esm_sampler.py:234)
+// E lives in shared memory (fp32, V*d*4 bytes) when it fits, else is read through L1/L2.
+// ---------------------------------------------------------------------------------------------
+struct HeadParams {
+  const float* g;        // [rows, d] fp32: gelu(dense(LN_after(x))) for the sampled rows
+  const float* ln_w;
+  const float* ln_b;
+  const float* emb;      // [V, d] tied projection weight
+  const float* out_bias; // [V]
+  float* logits_out;     // [rows, V] or nullptr
+  int32_t* tokens;       // [n_chains, T] or nullptr (no sampling: forward_logits)
+  int rows, d, V, T;
+  float eps;
+  Schedule sched;
+  int iter;
+  // sampler
+  const int32_t* valid_ids;  // [n_valid] (device)
+  int n_valid;
+  int top_k;                 // effective k for this iteration (already resolved against burn-in), <= n_valid
+  float temperature;         // <= 0 : none
+  const float* noise;        // replay: [rows, noise_stride] Exp(1) draws for this iteration, slot j <-> j-th largest
+  int noise_stride;
+  unsigned long long seed;   // device RNG otherwise
+  int emb_in_smem;
+  int skip_dup_writes;       // schedule may contain duplicate positions: last slot wins, like the reference loop
+};
+
+__global__ void __launch_bounds__(256) head_sample_kernel(HeadParams p) {
+  extern __shared__ float s_emb[];
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  if (p.emb_in_smem) {
+    const float4* src = reinterpret_cast<const float4*>(p.emb);
+    float4* dst = reinterpret_cast<float4*>(s_emb);
+    for (int i = threadIdx.x; i < (p.V * p.d) >> 2; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+  }
+  const float* E = p.emb_in_smem ? s_emb : p.emb;
+  const int nvec = p.d >> 2;
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < p.rows;
+       row += gridDim.x * warps_per_block) {
+    const float4* in = reinterpret_cast<const float4*>(p.g + static_cast<long long>(row) * p.d);
+    float4 v[kMaxVecPerLane];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLane; ++k) {
+      const int i = lane + k * 32;
+      if (i < nvec) {
+        v[k] = in[i];
+        sum += v[k].x + v[k].y + v[k].z + v[k].w;
+      }
+    }
+    const float mean = warp_sum(sum) / p.d;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLane; ++k) {
+      const int i = lane + k * 32;
+      if (i < nvec) {
+        const float4 a = v[k];
+        sq += (a.x - mean) * (a.x - mean) + (a.y - mean) * (a.y - mean) + (a.z - mean) * (a.z - mean) +
+              (a.w - mean) * (a.w - mean);
+      }
+    }
+    const float rstd = 1.0f / sqrtf(warp_sum(sq) / p.d + p.eps);
+#pragma unroll
+    for (int k = 0; k < kMaxVecPerLane; ++k) {
+      const int i = lane + k * 32;
+      if (i < nvec) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_w) + i);
+        const float4 h = __ldg(reinterpret_cast<const float4*>(p.ln_b) + i);
+        float4 a = v[k];
+        a.x = (a.x - mean) * rstd * g.x + h.x; a.y = (a.y - mean) * rstd * g.y + h.y;
+        a.z = (a.z - mean) * rstd * g.z + h.z; a.w = (a.w - mean) * rstd * g.w + h.w;
+        v[k] = a;
+      }
+    }
+    // vocabulary projection: lane v ends up holding logit v (v < 32); logit 32.. kept in `extra` on lane v-32
+    float mine = 0.f, extra = 0.f;
+    for (int tok = 0; tok < p.V; ++tok) {
+      const float4* e = reinterpret_cast<const float4*>(E + static_cast<long long>(tok) * p.d);
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < kMaxVecPerLane; ++k) {
+        const int i = lane + k * 32;
+        if (i < nvec) {
+          const float4 w = e[i];
+          acc = fmaf(v[k].x, w.x, acc); acc = fmaf(v[k].y, w.y, acc);
+          acc = fmaf(v[k].z, w.z, acc); acc = fmaf(v[k].w, w.w, acc);
+        }
+      }
+      acc = warp_sum(acc) + __ldg(p.out_bias + tok);
+      if ((tok & 31) == lane) { if (tok < 32) mine = acc; else extra = acc; }
+    }
+    if (p.logits_out) {
+      float* lo = p.logits_out + static_cast<long long>(row) * p.V;
+      if (lane < p.V) lo[lane] = mine;
+      if (lane + 32 < p.V) lo[lane + 32] = extra;
+    }
+    if (!p.tokens) continue;
+
+    const int best_id = generate_step_warp(mine, extra, lane, row, p.iter, p.valid_ids, p.n_valid, p.top_k,
+                                           p.temperature, p.noise, p.noise_stride, p.seed);
+    if (lane == 0) {
+      const int chain = row / p.sched.P, slot = row % p.sched.P;
+      const int32_t* plist = p.sched.positions + p.iter * p.sched.iter_stride + chain * p.sched.chain_stride;
+      const int pos = plist[slot];
+      bool write = true;
+      if (p.skip_dup_writes) {
+        for (int s2 = slot + 1; s2 < p.sched.P; ++s2) if (plist[s2] == pos) { write = false; break; }
+      }
+      if (write) p.tokens[(static_cast<long long>(chain) * p.sched.seq_stride + p.sched.seq_offset) * p.T + pos] = best_id;
+    }
+  }
+}
+
+}  // namespace pg

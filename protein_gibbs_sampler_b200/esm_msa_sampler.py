@@ -1,0 +1,224 @@
+"""ESM_MSA_sampler: the reference's MSA Gibbs sampler API on the B200 engine.
+
+Drop-in for /root/reference/src/pgen/esm_msa_sampler.py (class, methods, arguments, return values, error
+messages).  As in ``esm_sampler.py`` the host tokenises, pre-draws the position schedule with Python's
+``random`` in the reference's call order -- one ``random.sample`` per (MSA, row) per iteration (:272-279) --
+and the engine runs the loop body (:221-248, or :126-145 for ``generate_single``) on the GPU.
+"""
+import math
+import random
+from typing import Iterator, List, Tuple
+
+import numpy as np
+import torch
+from tqdm import trange
+
+from .esm_sampler import SchedulePlan, draw_replay_noise, generate_step, in_order_targets, parse_device  # noqa: F401
+
+ESM_MSA_ALLOWED_AMINO_ACIDS = "-ACDEFGHIKLMNPQRSTVWY"
+ESM_MSA_GAP_CHARACTERS = "-"
+
+
+def partition(input_list, num_partitions):
+    """Split into ``num_partitions`` consecutive bins; the remainder goes one-each to the first bins
+    (reference esm_msa_sampler.py:13-31, pinned by test_esm_msa_sampler.py:538-557)."""
+    n = len(input_list)
+    num_partitions = min(num_partitions, n)
+    if num_partitions <= 0:
+        return []
+    base, extra = divmod(n, num_partitions)
+    out, lo = [], 0
+    for i in range(num_partitions):
+        hi = lo + base + (1 if i < extra else 0)
+        out.append(list(input_list[lo:hi]))
+        lo = hi
+    return out
+
+
+class ESM_MSA_sampler():
+    def __init__(self, model, device="cpu", rng="device"):
+        if rng not in ("device", "replay"):
+            raise ValueError("rng must be 'device' or 'replay'")
+        self.model = model
+        self.rng = rng
+        self.model.model = self.model.model.eval()
+        self.device, self.cuda = parse_device(device)
+        self.model.model.to(self.device)
+        self.valid_aa_idx = sorted(self.model.alphabet.get_idx(tok) for tok in ESM_MSA_ALLOWED_AMINO_ACIDS)
+        self.toks = [self.model.alphabet.get_tok(idx) for idx in self.valid_aa_idx]
+
+    # ------------------------------------------------------------------ host helpers (reference API)
+    def untokenize_batch(self, batch):
+        """All rows of all MSAs, flattened in (msa, row) order, <cls> column dropped (:68-75)."""
+        msas = batch.tolist() if isinstance(batch, torch.Tensor) else batch
+        get_tok = self.model.alphabet.get_tok
+        return ["".join(get_tok(t) for t in row[1:]) for msa in msas for row in msa]
+
+    def clean_seed_seq(self, seq):
+        seq = seq.upper()
+        bad = set(seq) - set(ESM_MSA_ALLOWED_AMINO_ACIDS)
+        if bad:
+            raise Exception("Invalid input character: " + ",".join(bad))
+        return seq
+
+    def get_init_msa(self, seed_msa, max_len, batch_size=1):
+        padded = []
+        for i, seq in enumerate(seed_msa):
+            seq = self.clean_seed_seq(seq)
+            padded.append((str(i), seq + "<mask>" * (max_len - len(seq))))
+        return self.model.batch_converter([padded] * batch_size)[2]
+
+    def mask_target_indexes(self, batch, target_indexes):
+        mask_idx = self.model.alphabet.mask_idx
+        for b in range(len(batch)):
+            for r in range(len(batch[b])):
+                for kk in target_indexes[b][r]:
+                    batch[b][r][kk] = mask_idx
+
+    def mask_target_indexes_single(self, batch, target_indexes, seq_index):
+        mask_idx = self.model.alphabet.mask_idx
+        for b in range(len(batch)):
+            for kk in target_indexes:
+                batch[b][seq_index][kk] = mask_idx
+
+    def get_target_indexes_all_positions(self, batch_size, indexes, num_sequences):
+        return [[indexes] * num_sequences for _ in range(batch_size)]
+
+    def get_random_target_index(self, batch_size, indexes, num_positions, num_sequences):
+        return [[random.sample(indexes, num_positions) for _ in range(num_sequences)] for _ in range(batch_size)]
+
+    def get_target_index_in_order(self, batch_size, indexes, next_i, num_positions, num_sequences):
+        last_i, picked = in_order_targets(indexes, next_i, num_positions)
+        return last_i, [[picked] * num_sequences for _ in range(batch_size)]
+
+    def calculate_indexes(self, indexes, leader_length, max_len, rollover_from_start):
+        if indexes is not None:
+            return indexes, -1
+        indexes = list(range(1, max_len + 1))
+        if rollover_from_start:
+            return indexes, -1
+        return indexes[leader_length:], leader_length - 1
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _noise(self, engine, n_iters, rows, top_k, burnin):
+        if self.rng == "replay":
+            noise, stride = draw_replay_noise(n_iters, rows, len(self.valid_aa_idx), top_k, burnin)
+            engine.set_noise(noise, stride)
+        else:
+            engine.set_noise(None)
+            engine.set_device_rng(int(torch.randint(0, 2 ** 62, (1,)).item()))
+
+    def plan_positions(self, batch_size, num_sequences, indexes, last_i, num_positions, in_order, num_iters):
+        dup = len(set(indexes)) != len(indexes)
+        if num_positions <= 0:
+            return SchedulePlan(list(indexes), num_iters, len(indexes), 0, 0, dup), last_i
+        if in_order:
+            rows = []
+            for _ in range(num_iters):
+                last_i, picked = in_order_targets(indexes, last_i, num_positions)
+                rows.append(picked)
+            return SchedulePlan(rows, num_iters, num_positions, num_positions, 0, dup), last_i
+        pos = [self.get_random_target_index(batch_size, indexes, num_positions, num_sequences)
+               for _ in range(num_iters)]
+        n_chains = batch_size * num_sequences
+        return SchedulePlan(pos, num_iters, num_positions, n_chains * num_positions, num_positions, dup), last_i
+
+    # ------------------------------------------------------------------ generate
+    def generate(self, n_samples, seed_msa, batch_size=1, in_order=False, max_len=None, leader_length=0,
+                 leader_length_percent=None, top_k=0, temperature=None, num_iters=10, burnin=float('inf'),
+                 mask=True, num_positions=0, num_positions_percent=None, indexes=None, rollover_from_start=False,
+                 show_progress_bar=True):
+        """Resample every row of ``batch_size`` copies of the seed MSA (reference :151-253)."""
+        engine = self.model.model.require_engine()
+        num_sequences = len(seed_msa)
+        sequence_length = len(seed_msa[0])
+        n_rounds = math.ceil(n_samples / num_sequences / batch_size)
+        if num_positions_percent is not None:
+            num_positions = int(sequence_length * (num_positions_percent / 100))
+        num_positions = max(num_positions, 0)
+        if leader_length_percent is not None:
+            leader_length = int(sequence_length * (leader_length_percent / 100))
+        leader_length = max(leader_length, 0)
+        if max_len is None:
+            max_len = sequence_length
+
+        sequences = []
+        for rnd in trange(n_rounds, disable=(not show_progress_bar)):
+            batch = self.get_init_msa(seed_msa, max_len, batch_size)
+            indexes, last_i = self.calculate_indexes(indexes, leader_length, max_len, rollover_from_start)
+            num_positions = min(num_positions, len(indexes))
+            if num_iters > 0 and len(indexes) > 0:
+                plan, last_i = self.plan_positions(batch_size, num_sequences, indexes, last_i, num_positions,
+                                                   in_order, num_iters)
+                engine.set_tokens(batch)
+                engine.set_schedule(plan.positions, plan.n_iters, plan.P, plan.iter_stride, plan.chain_stride,
+                                    plan.has_duplicates)
+                self._noise(engine, plan.n_iters, batch_size * num_sequences * plan.P, top_k, burnin)
+                engine.run(0, plan.n_iters, burnin, top_k, temperature, mask, self.valid_aa_idx)
+                batch = engine.get_tokens()
+            out = self.untokenize_batch(batch)
+            sequences += out[0:n_samples - len(sequences)] if rnd == n_rounds - 1 else out
+        return sequences
+
+    def generate_single(self, seed_msa, steps=10, passes=3, burn_in=1, target_index=0, k=1, exclude_positions=None):
+        """One new sequence for row ``target_index`` (reference :101-147).  Each pass shuffles the positions,
+        splits them into ``steps`` bins; per bin the LAST row is masked (reference quirk, :133) and row
+        ``target_index`` is resampled at the bin's positions."""
+        engine = self.model.model.require_engine()
+        excluded = {i + 1 for i in (exclude_positions or [])}
+        sequence_length = len(seed_msa[0])
+        positions = [x for x in range(1, sequence_length + 1) if x not in excluded]
+        batch = self.get_init_msa(seed_msa, sequence_length, 1)
+        engine.set_tokens(batch)
+        for pass_num in range(passes):
+            random.shuffle(positions)
+            bins = partition(positions, steps)
+            i = 0
+            while i < len(bins):  # consecutive bins of equal size share one schedule upload
+                j = i
+                while j < len(bins) and len(bins[j]) == len(bins[i]):
+                    j += 1
+                group = bins[i:j]
+                P = len(group[0])
+                engine.set_schedule([p for b in group for p in b], len(group), P, P, 0, False)
+                burnin = float("inf") if pass_num < burn_in else 0
+                self._noise(engine, len(group), P, k, burnin)
+                engine.run_single(0, len(group), burnin, k, None, -1, target_index, self.valid_aa_idx)
+                i = j
+        return self.untokenize_batch(engine.get_tokens())[target_index]
+
+    # ------------------------------------------------------------------ scoring (shares the forward)
+    def log_likelihood(self, msa, target_index=0, with_masking=True, verbose=False, count_gaps=False,
+                       mask_distance=float("inf")) -> Tuple[float, List[float]]:
+        return next(self.log_likelihood_batch([msa], target_index, with_masking, verbose, count_gaps, mask_distance))
+
+    def log_likelihood_batch(self, msa_list, target_index=0, with_masking=True, verbose=False, count_gaps=False,
+                             mask_distance=float("inf"), batch_size=None) -> Iterator[Tuple[float, List[float]]]:
+        """Pseudo-log-likelihood of row ``target_index`` of each MSA (reference :319-432)."""
+        alphabet = self.model.alphabet
+        for msa in msa_list:
+            cleaned = [self.clean_seed_seq(s) for s in msa]
+            toks = self.model.batch_converter([(str(i), s) for i, s in enumerate(cleaned)])[2]  # [1,R,C]
+            target = cleaned[target_index]
+            L = len(target)
+            scored = [p for p in range(L) if count_gaps or target[p] not in ESM_MSA_GAP_CHARACTERS]
+            true_toks = toks[0, target_index]
+            vals = {}
+            if with_masking:
+                n_copies = int(min(mask_distance, L))
+                bs = batch_size or n_copies
+                for b0 in range(0, n_copies, bs):
+                    chunk = range(b0, min(b0 + bs, n_copies))
+                    t = toks.repeat(len(chunk), 1, 1)
+                    for j, i in enumerate(chunk):
+                        t[j, target_index, 1 + i:1 + L:n_copies] = alphabet.mask_idx
+                    lp = torch.log_softmax(self.model.model(t)["logits"], dim=-1)
+                    for j, i in enumerate(chunk):
+                        for pos in range(i, L, n_copies):
+                            vals[pos] = lp[j, target_index, 1 + pos, true_toks[1 + pos]].item()
+            else:
+                lp = torch.log_softmax(self.model.model(toks)["logits"], dim=-1)
+                for pos in range(L):
+                    vals[pos] = lp[0, target_index, 1 + pos, true_toks[1 + pos]].item()
+            ordered = [vals[p] for p in scored]
+            yield (float(sum(ordered) / max(len(ordered), 1)), ordered)

@@ -1,0 +1,264 @@
+"""ESM_sampler: the reference's single-sequence Gibbs sampler API on the B200 engine.
+
+Drop-in for /root/reference/src/pgen/esm_sampler.py: same class, method names, argument meaning, return
+values and error messages.  What changes is where the loop body runs.  The reference executes lines 209-234
+on the host (one forward, then one ``generate_step`` + host sync per residue); here the host only
+  1. tokenises the seeds                                   (get_init_seq, :104-126)
+  2. pre-draws the whole position schedule with Python's ``random`` in the reference's call order
+     (get_random_target_index / get_target_index_in_order, :242-257) -- bit-identical masking/indexing,
+  3. hands tokens + schedule to the engine, which runs all ``num_iters`` iterations on the GPU
+     (mask scatter -> transformer forward -> top-k/categorical draw -> write-back) without a host sync,
+  4. reads the tokens back and untokenises               (untokenize_batch, :84-93).
+
+Residue draws: ``rng="device"`` (default) uses the engine's Philox generator seeded from torch's global
+generator; ``rng="replay"`` pre-draws the Exp(1) variates ``Categorical.sample`` would consume from torch's
+CPU generator, in the reference's order, so that identical logits give identical residues.
+"""
+import math
+import random
+import re
+from typing import Iterator, List, Tuple
+
+import numpy as np
+import torch
+from tqdm import trange
+
+from . import engine as _engine
+
+ESM_ALLOWED_AMINO_ACIDS = "ACDEFGHIKLMNPQRSTVWY"
+
+
+def _effective_k(top_k, n_valid, sample):
+    return n_valid if (sample or top_k <= 0 or top_k > n_valid) else top_k
+
+
+def generate_step(out, gen_idx, temperature=None, top_k=0, sample=False, valid_idx=None, device_id=0):
+    """Draw one token id from ``out[gen_idx]`` (reference esm_sampler.py:8-45) with the engine's sampler
+    kernel.  The Exp(1) variates come from torch's global CPU generator exactly as ``Categorical.sample``
+    would draw them, so a seeded call reproduces the reference's choice.  Returns a 0-d LongTensor."""
+    logits = torch.as_tensor(out)[gen_idx].detach().float().cpu().reshape(1, -1)
+    if valid_idx is None:
+        valid_idx = list(range(logits.shape[1]))
+    k = _effective_k(top_k, len(valid_idx), sample)
+    noise = torch.ones(1, len(valid_idx))
+    noise[:, :k] = torch.empty(1, k).exponential_(1)
+    tok = _engine.op_sample(logits, noise, valid_idx, top_k=k, temperature=temperature, device_id=device_id)
+    return torch.tensor(int(tok[0]))
+
+
+def parse_device(device):
+    """Device-string grammar and errors of ESM_sampler.__init__ (reference esm_sampler.py:66-79)."""
+    if device == "gpu":
+        device = "cuda:0"
+    use_cuda = False
+    if re.match("^cuda:[0-9]+$", device):
+        if not torch.cuda.is_available():
+            raise Exception("gpu requested, but No Cuda devices found")
+        use_cuda = True
+        if int(device.split(":")[1]) >= torch.cuda.device_count():
+            raise Exception("Invalid cuda device number: " + device)
+    elif device != "cpu":
+        raise Exception("Invalid device: " + device)
+    return device, use_cuda
+
+
+def in_order_targets(indexes, next_i, num_positions):
+    """Cyclic cursor over ``indexes`` (reference :248-257): returns (last_i, picked positions)."""
+    picked = []
+    n = len(indexes)
+    for _ in range(num_positions):
+        next_i = (next_i + 1) % n
+        picked.append(indexes[next_i])
+    return next_i, picked
+
+
+class SchedulePlan:
+    """Positions for every iteration of one batch, laid out for pgibbs_set_schedule."""
+
+    def __init__(self, positions, n_iters, P, iter_stride, chain_stride, has_duplicates):
+        self.positions = np.ascontiguousarray(positions, dtype=np.int32).reshape(-1)
+        self.n_iters, self.P = n_iters, P
+        self.iter_stride, self.chain_stride = iter_stride, chain_stride
+        self.has_duplicates = has_duplicates
+
+    def targets(self, it, chain):
+        o = it * self.iter_stride + chain * self.chain_stride
+        return self.positions[o:o + self.P].tolist()
+
+
+def draw_replay_noise(n_iters, rows, n_valid, top_k, burnin):
+    """Exp(1) variates in the order the reference loop consumes them (iteration, chain, slot)."""
+    ks = [_effective_k(top_k, n_valid, it < burnin) for it in range(n_iters)]
+    stride = max(ks) if ks else 1
+    noise = torch.ones(n_iters, rows, stride)
+    for it, k in enumerate(ks):
+        noise[it, :, :k] = torch.empty(rows, k).exponential_(1)
+    return noise, stride
+
+
+class ESM_sampler():
+    """Gibbs sampler over single sequences; see module docstring."""
+
+    def __init__(self, model, device="cpu", rng="device"):
+        """model: object with ``model``, ``alphabet`` and ``batch_converter`` (see ``models.py``)."""
+        if rng not in ("device", "replay"):
+            raise ValueError("rng must be 'device' or 'replay'")
+        self.model = model
+        self.rng = rng
+        self.model.model = self.model.model.eval()
+        self.device, self.cuda = parse_device(device)
+        self.model.model.to(self.device)
+        self.valid_aa_idx = sorted(self.model.alphabet.get_idx(tok) for tok in ESM_ALLOWED_AMINO_ACIDS)
+
+    # ------------------------------------------------------------------ host helpers (reference API)
+    def untokenize_batch(self, batch, bos, eos):
+        lo = 1 if bos else 0
+        rows = batch.tolist() if isinstance(batch, torch.Tensor) else batch
+        get_tok = self.model.alphabet.get_tok
+        return ["".join(get_tok(t) for t in (row[lo:-1] if eos else row[lo:])) for row in rows]
+
+    @staticmethod
+    def clean_seed_seq(seed_to_clean):
+        cleaned = seed_to_clean.upper()
+        bad = set(cleaned) - set(ESM_ALLOWED_AMINO_ACIDS)
+        if bad:
+            raise Exception("Invalid input character: " + ",".join(bad))
+        return cleaned
+
+    def get_init_seq(self, seed_seq, max_len, batch_size=1):
+        """Seeds -> token tensor, right-filled with <mask> up to max_len (reference :104-126)."""
+        if isinstance(seed_seq, list):
+            chosen = random.choices(seed_seq, k=batch_size)
+            batch = [(str(i), self.clean_seed_seq(s) + "<mask>" * (max_len - len(s))) for i, s in enumerate(chosen)]
+        elif isinstance(seed_seq, str):
+            fill = "<mask>" * (max_len - len(seed_seq))
+            cleaned = self.clean_seed_seq(seed_seq)
+            batch = [(str(i), cleaned + fill) for i in range(batch_size)]
+        else:
+            raise Exception("seed sequence should either be a string or list")
+        return self.model.batch_converter(batch)[2]
+
+    def get_random_target_index(self, batch_size, indexes, num_positions):
+        return [random.sample(indexes, num_positions) for _ in range(batch_size)]
+
+    def get_target_index_in_order(self, batch_size, indexes, next_i, num_positions):
+        last_i, picked = in_order_targets(indexes, next_i, num_positions)
+        return last_i, [picked] * batch_size
+
+    def mask_target_indexes(self, batch, target_indexes):
+        mask_idx = self.model.alphabet.mask_idx
+        for b, targets in enumerate(target_indexes):
+            for kk in targets:
+                batch[b][kk] = mask_idx
+
+    def calculate_indexes(self, indexes, leader_length, max_len, rollover_from_start):
+        """Candidate positions and the in-order cursor, including the reference's cursor quirk (:264-274)."""
+        if indexes is not None:
+            return indexes, -1
+        indexes = range(1, max_len + 1)
+        if rollover_from_start:
+            return indexes, -1
+        return indexes[leader_length:], leader_length - 1
+
+    # ------------------------------------------------------------------ schedule
+    def plan_positions(self, batch_size, indexes, last_i, num_positions, in_order, num_iters):
+        """Pre-draw target positions for all iterations in the reference's RNG call order (:210-218)."""
+        dup = len(set(indexes)) != len(indexes)
+        if num_positions <= 0:
+            return SchedulePlan(list(indexes), num_iters, len(indexes), 0, 0, dup), last_i
+        if in_order:
+            rows = []
+            for _ in range(num_iters):
+                last_i, picked = in_order_targets(indexes, last_i, num_positions)
+                rows.append(picked)
+            return SchedulePlan(rows, num_iters, num_positions, num_positions, 0, dup), last_i
+        pos = [self.get_random_target_index(batch_size, indexes, num_positions) for _ in range(num_iters)]
+        return SchedulePlan(pos, num_iters, num_positions, batch_size * num_positions, num_positions, dup), last_i
+
+    # ------------------------------------------------------------------ generate
+    def generate(self, n_samples, seed_seq, batch_size=1, in_order=False, max_len=None, leader_length=0,
+                 leader_length_percent=None, top_k=0, temperature=None, num_iters=10, burnin=float('inf'),
+                 mask=True, num_positions=0, num_positions_percent=None, indexes=None, rollover_from_start=False,
+                 show_progress_bar=True):
+        """Generate ``n_samples`` sequences; arguments as in the reference (esm_sampler.py:128-172)."""
+        if isinstance(seed_seq, str):
+            sequence_length = len(seed_seq)
+        elif isinstance(seed_seq, list):
+            sequence_length = max(len(seed) for seed in seed_seq)
+        else:
+            raise ValueError("Unknown seed sequence format, expecting str or list")
+        engine = self.model.model.require_engine()
+        alphabet = self.model.alphabet
+
+        if max_len is None:
+            max_len = sequence_length
+        if num_positions_percent is not None:
+            num_positions = int(max_len * (num_positions_percent / 100))
+        num_positions = max(num_positions, 0)
+        if leader_length_percent is not None:
+            leader_length = int(max_len * (leader_length_percent / 100))
+        leader_length = max(leader_length, 0)
+
+        sequences = []
+        n_batches = math.ceil(n_samples / batch_size)
+        for batch_n in trange(n_batches, disable=(not show_progress_bar)):
+            batch = self.get_init_seq(seed_seq, max_len, batch_size)
+            indexes, last_i = self.calculate_indexes(indexes, leader_length, max_len, rollover_from_start)
+            num_positions = min(num_positions, len(indexes))
+            if num_iters > 0 and len(indexes) > 0:
+                plan, last_i = self.plan_positions(batch_size, indexes, last_i, num_positions, in_order, num_iters)
+                batch = self.run_plan(engine, batch, plan, top_k, temperature, burnin, mask)[:, 0]
+            keep = n_samples - len(sequences) if batch_n == n_batches - 1 else batch_size
+            sequences += self.untokenize_batch(batch, alphabet.prepend_bos, alphabet.append_eos)[0:keep]
+        return sequences
+
+    def run_plan(self, engine, tokens, plan, top_k, temperature, burnin, mask):
+        """Ship tokens + schedule to the GPU, run every iteration there, return the final tokens [B,R,T]."""
+        engine.set_tokens(tokens)
+        engine.set_schedule(plan.positions, plan.n_iters, plan.P, plan.iter_stride, plan.chain_stride,
+                            plan.has_duplicates)
+        n_chains = int(np.prod(tokens.shape[:-1]))
+        if self.rng == "replay":
+            noise, stride = draw_replay_noise(plan.n_iters, n_chains * plan.P, len(self.valid_aa_idx), top_k, burnin)
+            engine.set_noise(noise, stride)
+        else:
+            engine.set_noise(None)
+            engine.set_device_rng(int(torch.randint(0, 2 ** 62, (1,)).item()))
+        engine.run(0, plan.n_iters, burnin, top_k, temperature, mask, self.valid_aa_idx)
+        return engine.get_tokens()
+
+    # ------------------------------------------------------------------ scoring (shares the forward)
+    def log_likelihood(self, seq, with_masking=True, verbose=False, mask_distance=float("inf"),
+                       batch_size=None) -> Tuple[float, List[float]]:
+        return next(self.log_likelihood_batch([seq], with_masking, verbose, mask_distance, batch_size))
+
+    def log_likelihood_batch(self, seq_list, with_masking=True, verbose=False, mask_distance=float("inf"),
+                             batch_size=None) -> Iterator[Tuple[float, List[float]]]:
+        """Pseudo-log-likelihood with strided masking (reference :288-363).  Every forward here is over
+        equal-length rows, so no <pad> reaches the engine."""
+        alphabet = self.model.alphabet
+        if batch_size is None:
+            batch_size = len(seq_list)
+        start = 1 if alphabet.prepend_bos else 0
+        for seq in seq_list:
+            cleaned = self.clean_seed_seq(seq)
+            L = len(cleaned)
+            true_toks = self.model.batch_converter([("0", cleaned)])[2][0]
+            if with_masking:
+                n_copies = int(min(mask_distance, L))
+                toks = true_toks.repeat(n_copies, 1)
+                for i in range(n_copies):
+                    toks[i, start + i:start + L:n_copies] = alphabet.mask_idx
+                per_pos = [None] * L
+                for b0 in range(0, n_copies, batch_size):
+                    lp = torch.log_softmax(self.model.model(toks[b0:b0 + batch_size])["logits"], dim=-1)
+                    for j in range(lp.shape[0]):
+                        i = b0 + j
+                        for pos in range(i, L, n_copies):
+                            per_pos[pos] = lp[j, start + pos, true_toks[start + pos]].item()
+                # the reference accumulates copy by copy; keep its output ordering
+                ordered = [per_pos[pos] for i in range(n_copies) for pos in range(i, L, n_copies)]
+            else:
+                lp = torch.log_softmax(self.model.model(true_toks[None])["logits"], dim=-1)[0]
+                ordered = [lp[start + pos, true_toks[start + pos]].item() for pos in range(L)]
+            yield (float(sum(ordered) / L), ordered)

@@ -1,0 +1,55 @@
+"""Seeded synthetic weights in fair-esm state-dict naming.
+
+No pretrained checkpoint exists offline, so every model here is random-init:
+N(0, 0.02) linears/embeddings, LayerNorm weight 1 + small noise, small biases
+(SURVEY.md section 8d).  Keys match ``esm.pretrained`` state dicts after fair-esm's
+``upgrade_state_dict`` so a real checkpoint's ``model`` dict loads the same way.
+"""
+import torch
+
+
+def synthetic_state_dict(cfg, seed=0, std=0.02, ln_noise=0.02, bias_std=0.02):
+    g = torch.Generator().manual_seed(seed)
+    d, F, V, L = cfg["embed_dim"], cfg["ffn_dim"], cfg["vocab"], cfg["layers"]
+    sd = {}
+
+    def lin(prefix, n_out, n_in):
+        sd[prefix + ".weight"] = torch.randn(n_out, n_in, generator=g) * std
+        sd[prefix + ".bias"] = torch.randn(n_out, generator=g) * bias_std
+
+    def ln(prefix, n=d):
+        sd[prefix + ".weight"] = 1.0 + torch.randn(n, generator=g) * ln_noise
+        sd[prefix + ".bias"] = torch.randn(n, generator=g) * ln_noise
+
+    sd["embed_tokens.weight"] = torch.randn(V, d, generator=g) * std * 5
+    if cfg["positions"] == "learned":
+        tbl = torch.randn(cfg["max_positions"] + 2, d, generator=g) * std * 5
+        tbl[1].zero_()  # padding_idx row
+        sd["embed_positions.weight"] = tbl
+    if cfg["arch"] == "msa_transformer":
+        sd["msa_position_embedding"] = torch.randn(1, 1024, 1, d, generator=g) * 0.01 * 5
+    if cfg["emb_layer_norm_before"]:
+        ln("emb_layer_norm_before")
+    for i in range(L):
+        p = "layers.%d." % i
+        if cfg["arch"] == "msa_transformer":
+            for blk in ("row_self_attention", "column_self_attention"):
+                for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):
+                    lin(p + blk + ".layer." + nm, d, d)
+                ln(p + blk + ".layer_norm")
+            lin(p + "feed_forward_layer.layer.fc1", F, d)
+            lin(p + "feed_forward_layer.layer.fc2", d, F)
+            ln(p + "feed_forward_layer.layer_norm")
+        else:
+            for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):
+                lin(p + "self_attn." + nm, d, d)
+            ln(p + "self_attn_layer_norm")
+            lin(p + "fc1", F, d)
+            lin(p + "fc2", d, F)
+            ln(p + "final_layer_norm")
+    ln("emb_layer_norm_after")
+    lin("lm_head.dense", d, d)
+    ln("lm_head.layer_norm")
+    sd["lm_head.weight"] = sd["embed_tokens.weight"]  # tied (RobertaLMHead)
+    sd["lm_head.bias"] = torch.randn(V, generator=g) * bias_std
+    return sd
