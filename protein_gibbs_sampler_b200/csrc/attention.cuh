@@ -2,7 +2,7 @@
 //
 //   ctx[s, i, h, :] = softmax_j( q[s,i,h,:] . k[s,j,h,:] ) v[s,j,h,:]        (q is pre-scaled by Dh^-1/2,
 //                                                                             RoPE already applied by the QKV GEMM)
-// Flash-style: one CTA = 64 queries of one (sequence, head); keys/values stream through shared memory in
+// Flash-style: one CTA = 16*NWARPS queries of one (sequence, head); keys/values stream through shared memory in
 // 64-row chunks (cp.async double buffer); scores and the running softmax stay in registers in fp32.
 // No padding mask: the Gibbs path never contains <pad>.
 // Replaces fair-esm MultiheadAttention's bmm/softmax/bmm (call site /root/reference/src/pgen/esm_sampler.py:223).
@@ -57,17 +57,24 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Token t of attention group s lives in activation row
+//     (s / inner) * outer_stride + (s % inner) * inner_stride + t * row_step.
+// Sequence attention: inner=1, outer_stride=T, row_step=1.  MSA column attention (attend over the R rows of
+// one alignment column c of MSA b): s = b*C + c, inner=C, outer_stride=R*C, inner_stride=1, row_step=C, T=R.
 struct AttnParams {
-  const __half* qkv;  // [n_seq*T, ld]; q at col 0, k at col k_off, v at col v_off; head h at +h*DH
-  __half* ctx;        // [n_seq*T, ldc]
+  const __half* qkv;  // [rows, ld]; q at col 0, k at col k_off, v at col v_off; head h at +h*DH
+  __half* ctx;        // [rows, ldc]
   int T, ld, ldc, k_off, v_off;
+  int inner, inner_stride, row_step;
+  long long outer_stride;
 };
 
-constexpr int kAttnBQ = 64;   // queries per CTA (4 warps x 16)
 constexpr int kAttnBK = 64;   // keys per smem chunk
 
-template <int DH>
-__global__ void __launch_bounds__(128) attention_kernel(AttnParams p) {
+template <int DH, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32) attention_kernel(AttnParams p) {
+  constexpr int kAttnBQ = 16 * NWARPS;  // queries per CTA
+  constexpr int NT_ = NWARPS * 32;
   constexpr int LDS = DH + 8;          // padded row (halfs): 16-byte pad keeps ldmatrix conflict-free
   constexpr int CH = DH / 8;           // 16-byte chunks per row
   constexpr int KS = DH / 16;          // k-steps of QK^T
@@ -79,21 +86,23 @@ __global__ void __launch_bounds__(128) attention_kernel(AttnParams p) {
   const int seq = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * kAttnBQ;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const __half* base = p.qkv + static_cast<long long>(seq) * p.T * p.ld + head * DH;
+  const long long row0 = (seq / p.inner) * p.outer_stride + static_cast<long long>(seq % p.inner) * p.inner_stride;
+  const long long rs = static_cast<long long>(p.row_step) * p.ld;  // elements between consecutive tokens
+  const __half* base = p.qkv + row0 * p.ld + head * DH;
   const int n_chunks = (p.T + kAttnBK - 1) / kAttnBK;
 
   // Q tile
-  for (int i = tid; i < kAttnBQ * CH; i += 128) {
+  for (int i = tid; i < kAttnBQ * CH; i += NT_) {
     const int r = i / CH, c = i % CH;
     const bool ok = q0 + r < p.T;
-    cp_async16(&sQ[r * LDS + c * 8], base + static_cast<long long>(ok ? q0 + r : 0) * p.ld + c * 8, ok);
+    cp_async16(&sQ[r * LDS + c * 8], base + static_cast<long long>(ok ? q0 + r : 0) * rs + c * 8, ok);
   }
   auto load_kv = [&](int chunk, int buf) {
     const int k0 = chunk * kAttnBK;
-    for (int i = tid; i < kAttnBK * CH; i += 128) {
+    for (int i = tid; i < kAttnBK * CH; i += NT_) {
       const int r = i / CH, c = i % CH;
       const bool ok = k0 + r < p.T;
-      const __half* src = base + static_cast<long long>(ok ? k0 + r : 0) * p.ld + c * 8;
+      const __half* src = base + static_cast<long long>(ok ? k0 + r : 0) * rs + c * 8;
       cp_async16(&sK[buf][r * LDS + c * 8], src + p.k_off, ok);
       cp_async16(&sV[buf][r * LDS + c * 8], src + p.v_off, ok);
     }
@@ -196,12 +205,13 @@ __global__ void __launch_bounds__(128) attention_kernel(AttnParams p) {
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float i0 = 1.0f / l0, i1 = 1.0f / l1;
   const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
-  __half* out = p.ctx + static_cast<long long>(seq) * p.T * p.ldc + head * DH;
+  __half* out = p.ctx + row0 * p.ldc + head * DH;
+  const long long os = static_cast<long long>(p.row_step) * p.ldc;
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
     const int c = j * 8 + 2 * t4;
-    if (r0 < p.T) *reinterpret_cast<uint32_t*>(out + static_cast<long long>(r0) * p.ldc + c) = pack2(o[j][0] * i0, o[j][1] * i0);
-    if (r1 < p.T) *reinterpret_cast<uint32_t*>(out + static_cast<long long>(r1) * p.ldc + c) = pack2(o[j][2] * i1, o[j][3] * i1);
+    if (r0 < p.T) *reinterpret_cast<uint32_t*>(out + static_cast<long long>(r0) * os + c) = pack2(o[j][0] * i0, o[j][1] * i0);
+    if (r1 < p.T) *reinterpret_cast<uint32_t*>(out + static_cast<long long>(r1) * os + c) = pack2(o[j][2] * i1, o[j][3] * i1);
   }
 }
 

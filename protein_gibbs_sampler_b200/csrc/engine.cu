@@ -400,19 +400,33 @@ static int run_gemm(pgibbs_engine* e, const char* name, int epi, int bn, const C
   return launch_gemm(epi, bn, a, b, p, e->stream);
 }
 
-static int run_attention(pgibbs_engine* e) {
-  const int d = e->cfg.embed_dim, H = e->cfg.heads, hd = d / H;
-  AttnParams p{e->qkv, e->ctx, e->T, 3 * d, d, d, 2 * d};
-  dim3 grid((e->T + kAttnBQ - 1) / kAttnBQ, H, e->n_seq);
-  ProfScope ps(e, "attention");
-  switch (hd) {
-    case 16: attention_kernel<16><<<grid, 128, 0, e->stream>>>(p); break;
-    case 32: attention_kernel<32><<<grid, 128, 0, e->stream>>>(p); break;
-    case 64: attention_kernel<64><<<grid, 128, 0, e->stream>>>(p); break;
-    default: return fail("unsupported head_dim %d (16, 32, 64)", hd);
+static int launch_attention(const AttnParams& p, int groups, int H, int hd, cudaStream_t st) {
+  if (p.T <= 32) {  // short groups (MSA column attention over R <= 32 rows): 2 warps = 32 queries per CTA
+    dim3 grid((p.T + 31) / 32, H, groups);
+    switch (hd) {
+      case 16: attention_kernel<16, 2><<<grid, 64, 0, st>>>(p); break;
+      case 32: attention_kernel<32, 2><<<grid, 64, 0, st>>>(p); break;
+      case 64: attention_kernel<64, 2><<<grid, 64, 0, st>>>(p); break;
+      default: return fail("unsupported head_dim %d (16, 32, 64)", hd);
+    }
+  } else {
+    dim3 grid((p.T + 63) / 64, H, groups);
+    switch (hd) {
+      case 16: attention_kernel<16, 4><<<grid, 128, 0, st>>>(p); break;
+      case 32: attention_kernel<32, 4><<<grid, 128, 0, st>>>(p); break;
+      case 64: attention_kernel<64, 4><<<grid, 128, 0, st>>>(p); break;
+      default: return fail("unsupported head_dim %d (16, 32, 64)", hd);
+    }
   }
   CK(cudaGetLastError());
   return 0;
+}
+
+static int run_attention(pgibbs_engine* e) {
+  const int d = e->cfg.embed_dim, H = e->cfg.heads, hd = d / H;
+  AttnParams p{e->qkv, e->ctx, e->T, 3 * d, d, d, 2 * d, 1, 0, 1, e->T};
+  ProfScope ps(e, "attention");
+  return launch_attention(p, e->n_seq, H, hd, e->stream);
 }
 
 static GemmParams gp(int M, int N, int K, const float* bias, void* out, int ldo) {
@@ -468,7 +482,8 @@ static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int it
       TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->bn_qkv, e->m_h, l.m_cwqkv, qc));
       {
         ProfScope ps(e, "msa_col_attention");
-        if (const char* m = launch_msa_col_attention(e->qkv, e->ctx, e->B, e->R, e->T, c.heads, hd, st)) return fail("%s", m);
+        AttnParams ap{e->qkv, e->ctx, e->R, 3 * d, d, d, 2 * d, e->T, 1, e->T, static_cast<long long>(e->R) * e->T};
+        TRY(launch_attention(ap, e->B * e->T, c.heads, hd, st));
       }
       TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->bn_o, e->m_ctx, l.m_cwo, gp(M, d, d, l.c_bo, e->x, d)));
     } else {
@@ -951,15 +966,8 @@ int pgibbs_op_attention(int32_t device_id, const float* qkv, float* ctx, int32_t
     TRY(dev_alloc(&d32, nq)); TRY(dev_alloc(&d16, nq)); TRY(dev_alloc(&c32, nc)); TRY(dev_alloc(&c16, nc));
     CK(cudaMemcpy(d32, qkv, nq * sizeof(float), cudaMemcpyDefault));
     TRY(to_f16(d32, d16, nq, nullptr));
-    AttnParams p{d16, c16, T, 3 * d, d, d, 2 * d};
-    dim3 grid((T + kAttnBQ - 1) / kAttnBQ, heads, n_seq);
-    switch (head_dim) {
-      case 16: attention_kernel<16><<<grid, 128>>>(p); break;
-      case 32: attention_kernel<32><<<grid, 128>>>(p); break;
-      case 64: attention_kernel<64><<<grid, 128>>>(p); break;
-      default: return fail("unsupported head_dim %d", head_dim);
-    }
-    CK(cudaGetLastError());
+    AttnParams p{d16, c16, T, 3 * d, d, d, 2 * d, 1, 0, 1, T};
+    TRY(launch_attention(p, n_seq, heads, head_dim, nullptr));
     f16_to_f32_kernel<<<static_cast<unsigned>((nc + 255) / 256), 256>>>(c16, c32, nc);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());

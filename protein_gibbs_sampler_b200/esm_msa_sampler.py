@@ -123,13 +123,22 @@ class ESM_MSA_sampler():
         n_chains = batch_size * num_sequences
         return SchedulePlan(pos, num_iters, num_positions, n_chains * num_positions, num_positions, dup), last_i
 
+    def run_plan(self, tokens, plan, top_k, temperature, burnin, mask):
+        """Run every iteration of one round on the GPU; returns the final tokens [B,R,C].  No CPU path."""
+        engine = self.model.model.require_engine()
+        engine.set_tokens(tokens)
+        engine.set_schedule(plan.positions, plan.n_iters, plan.P, plan.iter_stride, plan.chain_stride,
+                            plan.has_duplicates)
+        self._noise(engine, plan.n_iters, tokens.shape[0] * tokens.shape[1] * plan.P, top_k, burnin)
+        engine.run(0, plan.n_iters, burnin, top_k, temperature, mask, self.valid_aa_idx)
+        return engine.get_tokens()
+
     # ------------------------------------------------------------------ generate
     def generate(self, n_samples, seed_msa, batch_size=1, in_order=False, max_len=None, leader_length=0,
                  leader_length_percent=None, top_k=0, temperature=None, num_iters=10, burnin=float('inf'),
                  mask=True, num_positions=0, num_positions_percent=None, indexes=None, rollover_from_start=False,
                  show_progress_bar=True):
         """Resample every row of ``batch_size`` copies of the seed MSA (reference :151-253)."""
-        engine = self.model.model.require_engine()
         num_sequences = len(seed_msa)
         sequence_length = len(seed_msa[0])
         n_rounds = math.ceil(n_samples / num_sequences / batch_size)
@@ -150,12 +159,7 @@ class ESM_MSA_sampler():
             if num_iters > 0 and len(indexes) > 0:
                 plan, last_i = self.plan_positions(batch_size, num_sequences, indexes, last_i, num_positions,
                                                    in_order, num_iters)
-                engine.set_tokens(batch)
-                engine.set_schedule(plan.positions, plan.n_iters, plan.P, plan.iter_stride, plan.chain_stride,
-                                    plan.has_duplicates)
-                self._noise(engine, plan.n_iters, batch_size * num_sequences * plan.P, top_k, burnin)
-                engine.run(0, plan.n_iters, burnin, top_k, temperature, mask, self.valid_aa_idx)
-                batch = engine.get_tokens()
+                batch = self.run_plan(batch, plan, top_k, temperature, burnin, mask)
             out = self.untokenize_batch(batch)
             sequences += out[0:n_samples - len(sequences)] if rnd == n_rounds - 1 else out
         return sequences

@@ -187,7 +187,6 @@ class ESM_sampler():
             sequence_length = max(len(seed) for seed in seed_seq)
         else:
             raise ValueError("Unknown seed sequence format, expecting str or list")
-        engine = self.model.model.require_engine()
         alphabet = self.model.alphabet
 
         if max_len is None:
@@ -207,13 +206,15 @@ class ESM_sampler():
             num_positions = min(num_positions, len(indexes))
             if num_iters > 0 and len(indexes) > 0:
                 plan, last_i = self.plan_positions(batch_size, indexes, last_i, num_positions, in_order, num_iters)
-                batch = self.run_plan(engine, batch, plan, top_k, temperature, burnin, mask)[:, 0]
+                batch = self.run_plan(batch, plan, top_k, temperature, burnin, mask)[:, 0]
             keep = n_samples - len(sequences) if batch_n == n_batches - 1 else batch_size
             sequences += self.untokenize_batch(batch, alphabet.prepend_bos, alphabet.append_eos)[0:keep]
         return sequences
 
-    def run_plan(self, engine, tokens, plan, top_k, temperature, burnin, mask):
-        """Ship tokens + schedule to the GPU, run every iteration there, return the final tokens [B,R,T]."""
+    def run_plan(self, tokens, plan, top_k, temperature, burnin, mask):
+        """Ship tokens + schedule to the GPU, run every iteration there, return the final tokens [B,R,T].
+        Raises if the model has no CUDA engine: there is no CPU path."""
+        engine = self.model.model.require_engine()
         engine.set_tokens(tokens)
         engine.set_schedule(plan.positions, plan.n_iters, plan.P, plan.iter_stride, plan.chain_stride,
                             plan.has_duplicates)

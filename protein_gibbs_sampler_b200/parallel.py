@@ -1,0 +1,33 @@
+"""Multi-GPU plumbing: chains (and whole MSAs) are independent Markov chains, so they shard across ranks with
+no data-path collective.  torch.distributed (NCCL on GPUs, gloo in CPU tests) is used only to ship the weights
+from rank 0 once and to gather the final token tensors."""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items, world_size, rank):
+    """Contiguous split of ``n_items`` chains (or MSAs -- never split one MSA's rows) over ranks."""
+    base, extra = divmod(n_items, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def broadcast_state_dict(sd, src=0, device="cpu"):
+    """Rank ``src`` holds ``sd``; every rank returns the same dict of fp32 tensors on ``device``."""
+    rank = dist.get_rank()
+    meta = [{k: tuple(v.shape) for k, v in sd.items()} if rank == src else None]
+    dist.broadcast_object_list(meta, src=src)
+    out = {}
+    for k, shape in meta[0].items():
+        t = sd[k].to(device=device, dtype=torch.float32).contiguous() if rank == src else \
+            torch.empty(shape, dtype=torch.float32, device=device)
+        dist.broadcast(t, src=src)
+        out[k] = t
+    return out
+
+
+def gather_sequences(local_seqs):
+    """All ranks' output strings in rank order (rank 0 gets the full list, others too)."""
+    bucket = [None] * dist.get_world_size()
+    dist.all_gather_object(bucket, list(local_seqs))
+    return [s for part in bucket for s in part]

@@ -1,0 +1,88 @@
+"""CPU-only checks of the C-ABI library (loads, exports every declared symbol, fails loudly without a GPU)
+and of the multi-rank plumbing (gloo, world_size 2)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from protein_gibbs_sampler_b200 import _lib, parallel
+from protein_gibbs_sampler_b200.config import get_config, tiny_config
+from protein_gibbs_sampler_b200.weights import synthetic_state_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "pgibbs.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(pgibbs_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), n
+    assert set(names) == set(_lib.SIGNATURES), set(names) ^ set(_lib.SIGNATURES)
+    assert b"sm_100a" in lib.pgibbs_version()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="CPU box behaviour")
+def test_create_fails_loudly_without_gpu():
+    lib = _lib.load()
+    cfg = _lib.ModelConfig(arch=1, layers=1, embed_dim=64, heads=2, ffn_dim=128, vocab=33, max_positions=1024,
+                           token_dropout=1, padding_idx=1, mask_idx=32, cls_idx=0, eos_idx=2)
+    h = ctypes.c_void_p()
+    assert lib.pgibbs_create(ctypes.byref(cfg), 0, ctypes.byref(h)) != 0
+    assert b"CUDA" in lib.pgibbs_last_error() or b"device" in lib.pgibbs_last_error()
+    with pytest.raises(_lib.EngineError):
+        _lib.check(lib.pgibbs_op_sample(0, None, None, 1, 33, None, 20, 0, -1.0, None))
+
+
+def test_algorithmic_flops_match_survey():
+    import bench
+    f = bench.algorithmic_flops_per_iter(get_config(bench.MODEL), 64, 258)
+    assert abs(f / 1e12 - 22.20) < 0.01
+
+
+def test_shard_range_covers_all_chains():
+    for n in (1, 7, 64, 512):
+        for w in (1, 2, 3, 8):
+            spans = [parallel.shard_range(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = tiny_config("esm2", 1, 64, 2, 128)
+    sd = synthetic_state_dict(cfg, 11) if rank == 0 else None
+    got = parallel.broadcast_state_dict(sd, src=0, device="cpu")
+    want = synthetic_state_dict(cfg, 11)
+    same = all(torch.equal(got[k], want[k]) for k in want) and set(got) == set(want)
+    lo, hi = parallel.shard_range(5, world, rank)
+    seqs = parallel.gather_sequences(["r%d_%d" % (rank, i) for i in range(lo, hi)])
+    q.put((rank, same, seqs))
+    dist.destroy_process_group()
+
+
+def test_weight_broadcast_and_gather_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res)
+    assert res[0][2] == res[1][2] == ["r0_0", "r0_1", "r0_2", "r1_3", "r1_4"]
