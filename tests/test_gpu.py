@@ -220,7 +220,7 @@ def test_full_size_properties_config2():
     rng = random.Random(1)
     seeds = ["".join(rng.choice("ACDEFGHIKLMNPQRSTVWY") for _ in range(256)) for _ in range(64)]
     m = models.ESM1b(seed=0)
-    s = ESM_sampler(m, device="cuda:0", rng="replay")
+    s = ESM_sampler(m, device="cuda:0", rng="device")   # Philox keyed by (iteration, chain, slot)
     toks = m.batch_converter([(str(i), x) for i, x in enumerate(seeds)])[2]
     eng = m.model.engine
     positions = sorted(random.Random(2).sample(range(1, 257), 40))
