@@ -216,6 +216,7 @@ struct pgibbs_engine {
   bool prof = false;
   std::map<std::string, ProfEntry> prof_acc;
   std::vector<std::tuple<std::string, cudaEvent_t, cudaEvent_t>> prof_pending;
+  std::vector<cudaEvent_t> event_pool;
   int64_t launches = 0;
 };
 
@@ -228,10 +229,22 @@ struct ProfScope {
   ProfScope(pgibbs_engine* e_, const char* n) : e(e_), name(n) {
     e->launches++;
     if (e->prof) {
-      cudaEventCreate(&a);
-      cudaEventCreate(&b);
+      a = take_event(e);
+      b = take_event(e);
       cudaEventRecord(a, e->stream);
     }
+  }
+  static cudaEvent_t take_event(pgibbs_engine* e) {
+    if (e->event_pool.empty()) {
+      for (int i = 0; i < 256; ++i) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        e->event_pool.push_back(ev);
+      }
+    }
+    cudaEvent_t ev = e->event_pool.back();
+    e->event_pool.pop_back();
+    return ev;
   }
   ~ProfScope() {
     if (e->prof) {
@@ -250,8 +263,8 @@ static int prof_flush(pgibbs_engine* e) {
     auto& acc = e->prof_acc[std::get<0>(t)];
     acc.ms += ms;
     acc.launches++;
-    cudaEventDestroy(std::get<1>(t));
-    cudaEventDestroy(std::get<2>(t));
+    e->event_pool.push_back(std::get<1>(t));
+    e->event_pool.push_back(std::get<2>(t));
   }
   e->prof_pending.clear();
   return 0;
@@ -544,12 +557,12 @@ static int check_ready(pgibbs_engine* e) {
 }
 
 static int upload_valid(pgibbs_engine* e, const int32_t* valid_ids, int n_valid) {
-  if (n_valid <= 0 || n_valid > 32) return fail("n_valid=%d out of range (1..32)", n_valid);
+  if (n_valid <= 0 || n_valid > 64) return fail("n_valid=%d out of range (1..64)", n_valid);
   std::vector<int32_t> v(n_valid);
   CK(cudaMemcpy(v.data(), valid_ids, n_valid * sizeof(int32_t), cudaMemcpyDefault));
   for (int i = 0; i < n_valid; ++i)
     if (v[i] < 0 || v[i] >= e->cfg.vocab) return fail("valid id %d outside vocabulary", v[i]);
-  if (!e->valid_dev) TRY(dev_alloc(&e->valid_dev, 32));
+  if (!e->valid_dev) TRY(dev_alloc(&e->valid_dev, 64));
   CK(cudaMemcpyAsync(e->valid_dev, v.data(), n_valid * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));  // v is a stack-backed vector
   return 0;
@@ -633,6 +646,7 @@ int pgibbs_destroy(pgibbs_engine* e) {
   if (e->noise) cudaFree(e->noise);
   if (e->valid_dev) cudaFree(e->valid_dev);
   for (auto& t : e->prof_pending) { cudaEventDestroy(std::get<1>(t)); cudaEventDestroy(std::get<2>(t)); }
+  for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
   return 0;
@@ -771,7 +785,7 @@ int pgibbs_set_noise(pgibbs_engine* e, const float* exp_noise, int64_t numel, in
   CK(cudaStreamSynchronize(e->stream));
   if (e->noise) { cudaFree(e->noise); e->noise = nullptr; e->noise_numel = 0; }
   if (!exp_noise || numel <= 0) return 0;
-  if (stride <= 0 || stride > 32) return fail("noise stride %d out of range", stride);
+  if (stride <= 0 || stride > 64) return fail("noise stride %d out of range", stride);
   TRY(dev_alloc(&e->noise, static_cast<size_t>(numel)));
   CK(cudaMemcpy(e->noise, exp_noise, numel * sizeof(float), cudaMemcpyDefault));
   e->noise_numel = numel;
@@ -984,7 +998,7 @@ int pgibbs_op_sample(int32_t device_id, const float* logits, const float* noise,
                      const int32_t* valid_ids, int32_t n_valid, int32_t top_k, float temperature,
                      int32_t* tokens_out) {
   TRY(op_device(device_id));
-  if (vocab > 64 || n_valid > 32 || n_valid <= 0) return fail("vocab <= 64 and 0 < n_valid <= 32 required");
+  if (vocab > 64 || n_valid > 64 || n_valid <= 0) return fail("vocab <= 64 and 0 < n_valid <= 64 required");
   float *dl = nullptr, *dn = nullptr;
   int32_t *dv = nullptr, *dout = nullptr;
   auto body = [&]() -> int {

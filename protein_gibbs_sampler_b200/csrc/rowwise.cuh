@@ -239,47 +239,54 @@ __device__ __forceinline__ int generate_step_warp(float mine, float extra, int l
                                                   const int32_t* __restrict__ valid_ids, int n, int k,
                                                   float temperature, const float* __restrict__ noise,
                                                   int noise_stride, unsigned long long seed) {
-  const int my_id = lane < n ? valid_ids[lane] : 0;
-  float l = __shfl_sync(0xffffffffu, mine, my_id & 31);
-  const float l_hi = __shfl_sync(0xffffffffu, extra, my_id & 31);
-  if (my_id >= 32) l = l_hi;
-  if (temperature > 0.f) l = __fdiv_rn(l, temperature);
-  if (lane >= n) l = -INFINITY;
+  // Up to 64 candidates: lane holds candidate slots `lane` (a) and `lane + 32` (b).
+  const bool has_a = lane < n, has_b = lane + 32 < n;
+  const int id_a = has_a ? valid_ids[lane] : 0, id_b = has_b ? valid_ids[lane + 32] : 0;
+  auto fetch = [&](int id) {
+    const float lo = __shfl_sync(0xffffffffu, mine, id & 31);
+    const float hi = __shfl_sync(0xffffffffu, extra, id & 31);
+    return id >= 32 ? hi : lo;
+  };
+  float la = fetch(id_a), lb = fetch(id_b);
+  if (temperature > 0.f) { la = __fdiv_rn(la, temperature); lb = __fdiv_rn(lb, temperature); }
+  if (!has_a) la = -INFINITY;
+  if (!has_b) lb = -INFINITY;
   // rank = position in the descending top-k order (ties: lower candidate slot first)
-  int rank = 0;
+  int rank_a = 0, rank_b = 0;
   for (int j = 0; j < n; ++j) {
-    const float o = __shfl_sync(0xffffffffu, l, j);
-    rank += (o > l) || (o == l && j < lane);
+    const float oa = __shfl_sync(0xffffffffu, la, j & 31), ob = __shfl_sync(0xffffffffu, lb, j & 31);
+    const float o = j < 32 ? oa : ob;
+    rank_a += (o > la) || (o == la && j < lane);
+    rank_b += (o > lb) || (o == lb && j < lane + 32);
   }
-  const bool in_top = lane < n && rank < k;
+  const bool top_a = has_a && rank_a < k, top_b = has_b && rank_b < k;
   // Categorical.__init__: logits - logsumexp(logits); .probs = softmax(that)
-  float mx = in_top ? l : -INFINITY;
+  float mx = fmaxf(top_a ? la : -INFINITY, top_b ? lb : -INFINITY);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-  const float ex = in_top ? expf(l - mx) : 0.f;
-  const float lse = logf(warp_sum(ex)) + mx;
-  const float ln = l - lse;                       // normalised logits
-  float mx2 = in_top ? ln : -INFINITY;
+  const float lse = logf(warp_sum((top_a ? expf(la - mx) : 0.f) + (top_b ? expf(lb - mx) : 0.f))) + mx;
+  const float na = la - lse, nb = lb - lse;  // normalised logits
+  float mx2 = fmaxf(top_a ? na : -INFINITY, top_b ? nb : -INFINITY);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx2 = fmaxf(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
-  const float ex2 = in_top ? expf(ln - mx2) : 0.f;
-  const float prob = __fdiv_rn(ex2, warp_sum(ex2));
-  float q = 1.f;
-  if (in_top) {
-    if (noise) {
-      q = noise[static_cast<long long>(row) * noise_stride + rank];
-    } else {
-      const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(iter), static_cast<uint32_t>(row),
-                                               static_cast<uint32_t>(rank), 0x5eedu),
-                                    make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
-      const float u = (static_cast<float>(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
-      q = -logf(u);
-    }
-  }
-  float score = in_top ? __fdiv_rn(prob, q) : -INFINITY;
+  const float ea = top_a ? expf(na - mx2) : 0.f, eb = top_b ? expf(nb - mx2) : 0.f;
+  const float denom = warp_sum(ea + eb);
+  auto draw = [&](int rank) {
+    if (noise) return noise[static_cast<long long>(row) * noise_stride + rank];
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(iter), static_cast<uint32_t>(row),
+                                             static_cast<uint32_t>(rank), 0x5eedu),
+                                  make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    const float u = (static_cast<float>(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+    return -logf(u);
+  };
+  const float sa = top_a ? __fdiv_rn(__fdiv_rn(ea, denom), draw(rank_a)) : -INFINITY;
+  const float sb = top_b ? __fdiv_rn(__fdiv_rn(eb, denom), draw(rank_b)) : -INFINITY;
   // argmax over slots; ties -> lowest rank (torch.argmax returns the first maximum)
-  int best_rank = in_top ? rank : 0x7fffffff;
-  int best_id = my_id;
+  const int ra = top_a ? rank_a : 0x7fffffff, rb = top_b ? rank_b : 0x7fffffff;
+  const bool pick_b = sb > sa || (sb == sa && rb < ra);
+  float score = pick_b ? sb : sa;
+  int best_rank = pick_b ? rb : ra;
+  int best_id = pick_b ? id_b : id_a;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float os = __shfl_xor_sync(0xffffffffu, score, o);

@@ -17,6 +17,7 @@ CPU generator, in the reference's order, so that identical logits give identical
 import math
 import random
 import re
+import time
 from typing import Iterator, List, Tuple
 
 import numpy as np
@@ -109,6 +110,7 @@ class ESM_sampler():
         self.device, self.cuda = parse_device(device)
         self.model.model.to(self.device)
         self.valid_aa_idx = sorted(self.model.alphabet.get_idx(tok) for tok in ESM_ALLOWED_AMINO_ACIDS)
+        self.last_timing = {}
 
     # ------------------------------------------------------------------ host helpers (reference API)
     def untokenize_batch(self, batch, bos, eos):
@@ -214,6 +216,7 @@ class ESM_sampler():
     def run_plan(self, tokens, plan, top_k, temperature, burnin, mask):
         """Ship tokens + schedule to the GPU, run every iteration there, return the final tokens [B,R,T].
         Raises if the model has no CUDA engine: there is no CPU path."""
+        t0 = time.perf_counter()
         engine = self.model.model.require_engine()
         engine.set_tokens(tokens)
         engine.set_schedule(plan.positions, plan.n_iters, plan.P, plan.iter_stride, plan.chain_stride,
@@ -225,8 +228,14 @@ class ESM_sampler():
         else:
             engine.set_noise(None)
             engine.set_device_rng(int(torch.randint(0, 2 ** 62, (1,)).item()))
+        t1 = time.perf_counter()
         engine.run(0, plan.n_iters, burnin, top_k, temperature, mask, self.valid_aa_idx)
-        return engine.get_tokens()
+        t2 = time.perf_counter()
+        out = engine.get_tokens()
+        t3 = time.perf_counter()
+        # host-side trace of the last batch (the reference has no tracing; this is the engine's)
+        self.last_timing = {"upload_s": t1 - t0, "enqueue_s": t2 - t1, "wait_and_download_s": t3 - t2}
+        return out
 
     # ------------------------------------------------------------------ scoring (shares the forward)
     def log_likelihood(self, seq, with_masking=True, verbose=False, mask_distance=float("inf"),
