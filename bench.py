@@ -207,7 +207,10 @@ def run_ours(args):
     sampler = ESM_sampler(model, device="cuda:%d" % local, rng="device")
     del sd
     engine = model.model.engine
-    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+    # time on the stream the kernels are launched on: a dedicated torch stream shared with the engine
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    engine.set_stream(stream.cuda_stream)
 
     B, T = CHAINS_PER_GPU, SEQ_LEN + 2
     K, W = args.steps, args.warmup
@@ -233,11 +236,15 @@ def run_ours(args):
         clocks.start()
     launches0 = engine.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
+    t_host0 = time.perf_counter()
+    ev0.record(stream)
     engine.run(W, K, BURNIN, TOP_K, None, True, sampler.valid_aa_idx)
-    ev1.record()
+    ev1.record(stream)
     barrier()
+    host_ms = (time.perf_counter() - t_host0) * 1000.0
     ms = ev0.elapsed_time(ev1)
+    # the device interval can never exceed the host wall clock around it by more than jitter
+    assert ms <= host_ms * 1.05 + 1.0 and ms >= 0.5 * host_ms, (ms, host_ms)
     launches = engine.launch_count() - launches0
     clock_info = clocks.stop() if rank == 0 else None
     if world > 1:
@@ -269,8 +276,10 @@ def run_ours(args):
     # ---- per-kernel-class timing (separate pass with CUDA events around every launch) for the roofline
     roofline = None
     if rank == 0:
-        engine.profile_enable(True)
         n_prof = min(K, 5)
+        engine.set_tokens(tokens)
+        engine.set_schedule(plan.positions, plan.n_iters, plan.P, plan.iter_stride, plan.chain_stride)
+        engine.profile_enable(True)
         engine.run(W, n_prof, BURNIN, TOP_K, None, True, sampler.valid_aa_idx)
         engine.sync()
         prof = engine.profile_read()

@@ -37,8 +37,9 @@ const char* pgibbs_version(void);
  * (esm_sampler.py:68-80, esm_msa_sampler.py:51-63).  Fails if no sm_100 GPU is present. */
 int pgibbs_create(const pgibbs_model_config* cfg, int32_t device_id, pgibbs_engine** out);
 int pgibbs_destroy(pgibbs_engine* e);
-/* Launch on the caller's CUDA stream (cudaStream_t) instead of the engine's own. */
-int pgibbs_set_stream(pgibbs_engine* e, void* cuda_stream);
+/* external != 0: launch on the caller's CUDA stream `cuda_stream` (a cudaStream_t; NULL is the CUDA default
+ * stream).  external == 0: back to the engine's own non-blocking stream. */
+int pgibbs_set_stream(pgibbs_engine* e, void* cuda_stream, int32_t external);
 
 /* One fp32 tensor of the fair-esm state dict by key name (models.py:61-86 bind the loaders). */
 int pgibbs_load_weight(pgibbs_engine* e, const char* name, const float* data, int64_t numel);

@@ -26,7 +26,7 @@ SIGNATURES = {
     "pgibbs_version": (c_char_p, []),
     "pgibbs_create": (c_i32, [P(ModelConfig), c_i32, P(c_void_p)]),
     "pgibbs_destroy": (c_i32, [c_void_p]),
-    "pgibbs_set_stream": (c_i32, [c_void_p, c_void_p]),
+    "pgibbs_set_stream": (c_i32, [c_void_p, c_void_p, c_i32]),
     "pgibbs_load_weight": (c_i32, [c_void_p, c_char_p, c_void_p, c_i64]),
     "pgibbs_finalize_weights": (c_i32, [c_void_p]),
     "pgibbs_set_tokens": (c_i32, [c_void_p, c_void_p, c_i32, c_i32, c_i32]),

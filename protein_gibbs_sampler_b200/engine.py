@@ -63,7 +63,12 @@ class Engine:
 
     # ---- state
     def set_stream(self, cuda_stream_ptr):
-        check(self.lib.pgibbs_set_stream(self.h, ctypes.c_void_p(cuda_stream_ptr)))
+        """Launch on an external CUDA stream (e.g. ``torch.cuda.current_stream().cuda_stream``; 0 is the CUDA
+        default stream).  ``None`` returns to the engine's own stream."""
+        if cuda_stream_ptr is None:
+            check(self.lib.pgibbs_set_stream(self.h, None, 0))
+        else:
+            check(self.lib.pgibbs_set_stream(self.h, ctypes.c_void_p(cuda_stream_ptr), 1))
 
     def set_tokens(self, tokens):
         t = torch.as_tensor(tokens)
