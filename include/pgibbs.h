@@ -102,7 +102,8 @@ int64_t pgibbs_launch_count(pgibbs_engine* e);
  * gemm: C[M,N] = epi(A[M,K] . B[N,K]^T + bias) with fp32 host/device inputs rounded to fp16 operands.
  * epilogue: 0 bias->fp16, 1 gelu->fp16, 2 residual add into C (fp32), 4 gelu->fp32, 5 bias->fp32. */
 int pgibbs_op_gemm(int32_t device_id, const float* A, const float* B, const float* bias, float* C, int32_t M,
-                   int32_t N, int32_t K, int32_t epilogue, int32_t block_n, float* elapsed_ms, int32_t reps);
+                   int32_t N, int32_t K, int32_t epilogue, int32_t block_n, int32_t cta_group, float* elapsed_ms,
+                   int32_t reps);
 /* attention over fused qkv [n_seq*T, 3*heads*head_dim] (fp32 in, rounded to fp16) -> ctx [n_seq*T, heads*head_dim]. */
 int pgibbs_op_attention(int32_t device_id, const float* qkv, float* ctx, int32_t n_seq, int32_t T, int32_t heads,
                         int32_t head_dim);

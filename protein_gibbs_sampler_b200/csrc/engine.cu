@@ -78,63 +78,98 @@ static int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t
 // ------------------------------------------------------------------------------------- GEMM launch
 static int g_num_sms = 0;
 
-template <int BN, int EPI>
+// A GEMM's tiling: tile width and whether a CTA pair (cta_group::2, 256-row tiles) computes it.
+// The B tensor map's box holds bn / cg rows.
+struct GemmPlan {
+  int bn = 256, cg = 2;
+  int b_box() const { return bn / cg; }
+};
+
+template <int BN, int EPI, int CG>
 static int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    CK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            gemm_smem_bytes(BN)));
+    CK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                            gemm_smem_bytes(BN, CG)));
     configured = true;
   }
-  const int m_tiles = (p.M + kBM - 1) / kBM, n_tiles = (p.N + BN - 1) / BN;
-  const int grid = std::min(g_num_sms, m_tiles * n_tiles);
-  gemm_tcgen05_kernel<BN, EPI><<<grid, kGemmThreads, gemm_smem_bytes(BN), st>>>(a, b, p);
-  CK(cudaGetLastError());
+  const int m_tiles = (p.M + kBM * CG - 1) / (kBM * CG), n_tiles = (p.N + BN - 1) / BN;
+  const int groups = std::min(g_num_sms / CG, m_tiles * n_tiles);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(groups * CG);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = gemm_smem_bytes(BN, CG);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG>, a, b, p));
   return 0;
 }
 
 template <int EPI>
-static int launch_gemm_bn(int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
-  switch (bn) {
-    case 64: return launch_gemm_inst<64, EPI>(a, b, p, st);
-    case 128: return launch_gemm_inst<128, EPI>(a, b, p, st);
-    case 192: return launch_gemm_inst<192, EPI>(a, b, p, st);
-    case 256: return launch_gemm_inst<256, EPI>(a, b, p, st);
+static int launch_gemm_bn(GemmPlan g, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p,
+                          cudaStream_t st) {
+  if (g.cg == 2) {
+    switch (g.bn) {
+      case 128: return launch_gemm_inst<128, EPI, 2>(a, b, p, st);
+      case 192: return launch_gemm_inst<192, EPI, 2>(a, b, p, st);
+      case 256: return launch_gemm_inst<256, EPI, 2>(a, b, p, st);
+    }
+  } else if (g.cg == 1) {
+    switch (g.bn) {
+      case 64: return launch_gemm_inst<64, EPI, 1>(a, b, p, st);
+      case 128: return launch_gemm_inst<128, EPI, 1>(a, b, p, st);
+      case 192: return launch_gemm_inst<192, EPI, 1>(a, b, p, st);
+      case 256: return launch_gemm_inst<256, EPI, 1>(a, b, p, st);
+    }
   }
-  return fail("unsupported GEMM block_n %d", bn);
+  return fail("unsupported GEMM tiling block_n=%d cta_group=%d", g.bn, g.cg);
 }
 
-static int launch_gemm(int epi, int bn, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p,
+static int launch_gemm(int epi, GemmPlan g, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p,
                        cudaStream_t st) {
   if (p.K % kBK) return fail("GEMM K=%d must be a multiple of %d", p.K, kBK);
   if (p.N % 16) return fail("GEMM N=%d must be a multiple of 16", p.N);
   switch (epi) {
-    case EPI_BIAS_F16: return launch_gemm_bn<EPI_BIAS_F16>(bn, a, b, p, st);
-    case EPI_GELU_F16: return launch_gemm_bn<EPI_GELU_F16>(bn, a, b, p, st);
-    case EPI_RESID_F32: return launch_gemm_bn<EPI_RESID_F32>(bn, a, b, p, st);
-    case EPI_QKV_F16: return launch_gemm_bn<EPI_QKV_F16>(bn, a, b, p, st);
-    case EPI_GELU_F32: return launch_gemm_bn<EPI_GELU_F32>(bn, a, b, p, st);
-    case EPI_BIAS_F32: return launch_gemm_bn<EPI_BIAS_F32>(bn, a, b, p, st);
+    case EPI_BIAS_F16: return launch_gemm_bn<EPI_BIAS_F16>(g, a, b, p, st);
+    case EPI_GELU_F16: return launch_gemm_bn<EPI_GELU_F16>(g, a, b, p, st);
+    case EPI_RESID_F32: return launch_gemm_bn<EPI_RESID_F32>(g, a, b, p, st);
+    case EPI_QKV_F16: return launch_gemm_bn<EPI_QKV_F16>(g, a, b, p, st);
+    case EPI_GELU_F32: return launch_gemm_bn<EPI_GELU_F32>(g, a, b, p, st);
+    case EPI_BIAS_F32: return launch_gemm_bn<EPI_BIAS_F32>(g, a, b, p, st);
   }
   return fail("unsupported GEMM epilogue %d", epi);
 }
 
-// Tile width: least estimated time on the persistent grid = waves x BN / efficiency(BN).  Narrow tiles re-read
-// the A operand from shared memory more often per FLOP (measured on B200: 1143 / 1100 / 884 TFLOP/s at
-// BN = 256 / 192 / 128 for M=16512, K=1280), so they only win when they remove a whole wave.
-static int pick_block_n(int M, int N, int multiple_of) {
+// Tiling choice: least estimated time on the persistent grid = waves x BN / efficiency.  Narrow tiles re-read the
+// A operand from shared memory more often per FLOP, so they only win when they remove a whole wave.  CTA pairs
+// (256-row tiles, half the operand bytes per SM) are used whenever the problem has more than one 128-row block;
+// `g_force_cg` (PGIBBS_GEMM_CG=1|2) pins the choice for A/B measurements.
+static int g_force_cg = 0;
+static GemmPlan pick_gemm_plan(int M, int N, int multiple_of) {
   static const int cands[] = {256, 192, 128, 64};
-  static const double eff[] = {1.0, 0.95, 0.77, 0.45};
-  const int m_tiles = (M + kBM - 1) / kBM;
+  static const double eff1[] = {1.0, 0.95, 0.77, 0.45};   // measured, single CTA (B200, M=16512, K=1280)
+  static const double eff2[] = {1.0, 0.97, 0.90, 0.0};    // CTA pair: operand traffic is no longer the limit
+  GemmPlan best;
   double best_cost = -1;
-  int best = 64;
-  for (int i = 0; i < 4; ++i) {
-    const int bn = cands[i];
-    if (bn % multiple_of) continue;
-    const long tiles = static_cast<long>(m_tiles) * ((N + bn - 1) / bn);
-    const long waves = (tiles + g_num_sms - 1) / g_num_sms;
-    const double cost = static_cast<double>(waves) * bn / eff[i];
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = bn; }
+  for (int cg = 2; cg >= 1; --cg) {
+    if (g_force_cg && cg != g_force_cg) continue;
+    if (!g_force_cg && cg == 2 && M <= kBM) continue;
+    const int m_tiles = (M + kBM * cg - 1) / (kBM * cg);
+    const int slots = g_num_sms / cg;
+    for (int i = 0; i < 4; ++i) {
+      const int bn = cands[i];
+      if (bn % multiple_of) continue;
+      const double eff = (cg == 2 ? eff2[i] : eff1[i]) * (cg == 2 ? 1.3 : 1.0);
+      if (eff <= 0) continue;
+      const long tiles = static_cast<long>(m_tiles) * ((N + bn - 1) / bn);
+      const long waves = (tiles + slots - 1) / slots;
+      const double cost = static_cast<double>(waves) * bn * cg / eff;
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best.bn = bn; best.cg = cg; }
+    }
   }
   return best;
 }
@@ -203,7 +238,7 @@ struct pgibbs_engine {
   __half *h = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr, *hs = nullptr;
   float *g = nullptr, *logits = nullptr, *scores = nullptr;
   CUtensorMap m_h, m_ctx, m_ffn, m_hs;
-  int bn_qkv = 256, bn_o = 256, bn_fc1 = 256, bn_fc2 = 256, bn_dense = 256;
+  GemmPlan g_qkv, g_o, g_fc1, g_fc2, g_dense;
   // schedule / rng
   int32_t* positions = nullptr;
   int64_t positions_numel = 0, positions_used = 0;
@@ -336,16 +371,16 @@ static int free_activations(pgibbs_engine* e) {
 static int build_weight_maps(pgibbs_engine* e) {
   const int d = e->cfg.embed_dim, F = e->cfg.ffn_dim;
   for (auto& l : e->L) {
-    TRY(make_tmap_2d(&l.m_wqkv, l.wqkv, 3 * d, d, d, e->bn_qkv));
-    TRY(make_tmap_2d(&l.m_wo, l.wo, d, d, d, e->bn_o));
-    TRY(make_tmap_2d(&l.m_w1, l.w1, F, d, d, e->bn_fc1));
-    TRY(make_tmap_2d(&l.m_w2, l.w2, d, F, F, e->bn_fc2));
+    TRY(make_tmap_2d(&l.m_wqkv, l.wqkv, 3 * d, d, d, e->g_qkv.b_box()));
+    TRY(make_tmap_2d(&l.m_wo, l.wo, d, d, d, e->g_o.b_box()));
+    TRY(make_tmap_2d(&l.m_w1, l.w1, F, d, d, e->g_fc1.b_box()));
+    TRY(make_tmap_2d(&l.m_w2, l.w2, d, F, F, e->g_fc2.b_box()));
     if (e->cfg.arch == PGIBBS_ARCH_MSA) {
-      TRY(make_tmap_2d(&l.m_cwqkv, l.c_wqkv, 3 * d, d, d, e->bn_qkv));
-      TRY(make_tmap_2d(&l.m_cwo, l.c_wo, d, d, d, e->bn_o));
+      TRY(make_tmap_2d(&l.m_cwqkv, l.c_wqkv, 3 * d, d, d, e->g_qkv.b_box()));
+      TRY(make_tmap_2d(&l.m_cwo, l.c_wo, d, d, d, e->g_o.b_box()));
     }
   }
-  TRY(make_tmap_2d(&e->m_wdense, e->w_dense, d, d, d, e->bn_dense));
+  TRY(make_tmap_2d(&e->m_wdense, e->w_dense, d, d, d, e->g_dense.b_box()));
   return 0;
 }
 
@@ -382,11 +417,11 @@ static int ensure_shape(pgibbs_engine* e, int B, int R, int T) {
   TRY(make_tmap_2d(&e->m_ffn, e->ffn, M, F, F, kBM));
   TRY(make_tmap_2d(&e->m_hs, e->hs, M, d, d, kBM));
   const int hd = d / e->cfg.heads;
-  e->bn_qkv = pick_block_n(e->M, 3 * d, hd >= 64 ? 64 : 32);
-  e->bn_o = pick_block_n(e->M, d, 16);
-  e->bn_fc1 = pick_block_n(e->M, F, 16);
-  e->bn_fc2 = pick_block_n(e->M, d, 16);
-  e->bn_dense = pick_block_n(e->M, d, 16);
+  e->g_qkv = pick_gemm_plan(e->M, 3 * d, hd >= 64 ? 64 : 32);
+  e->g_o = pick_gemm_plan(e->M, d, 16);
+  e->g_fc1 = pick_gemm_plan(e->M, F, 16);
+  e->g_fc2 = pick_gemm_plan(e->M, d, 16);
+  e->g_dense = pick_gemm_plan(e->M, d, 16);
   TRY(build_weight_maps(e));
   if (e->cfg.arch == PGIBBS_ARCH_ESM2 && e->rope_T < T) {
     if (e->rope) cudaFree(e->rope);
@@ -411,10 +446,10 @@ static int run_ln(pgibbs_engine* e, const float* x, const float* w, const float*
   return 0;
 }
 
-static int run_gemm(pgibbs_engine* e, const char* name, int epi, int bn, const CUtensorMap& a, const CUtensorMap& b,
-                    GemmParams p) {
+static int run_gemm(pgibbs_engine* e, const char* name, int epi, GemmPlan g, const CUtensorMap& a,
+                    const CUtensorMap& b, GemmParams p) {
   ProfScope ps(e, name);
-  return launch_gemm(epi, bn, a, b, p, e->stream);
+  return launch_gemm(epi, g, a, b, p, e->stream);
 }
 
 static int launch_attention(const AttnParams& p, int groups, int H, int hd, cudaStream_t st) {
@@ -484,44 +519,44 @@ static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int it
       TRY(run_ln(e, e->x, l.ln1w, l.ln1b, e->h, M, nullptr, 0));
       GemmParams q = gp(M, 3 * d, d, l.bqkv, e->qkv, 3 * d);
       q.q_cols = d; q.q_scale = row_scale; q.rope_cols = 0; q.head_dim = hd; q.seq_len = e->T;
-      TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->bn_qkv, e->m_h, l.m_wqkv, q));
+      TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->g_qkv, e->m_h, l.m_wqkv, q));
       {
         ProfScope ps(e, "msa_row_attention");
         if (const char* m = launch_msa_row_attention(e->qkv, e->ctx, e->scores, e->B, e->R, e->T, c.heads, hd, st)) return fail("%s", m);
       }
-      TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->bn_o, e->m_ctx, l.m_wo, gp(M, d, d, l.bo, e->x, d)));
+      TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->g_o, e->m_ctx, l.m_wo, gp(M, d, d, l.bo, e->x, d)));
       // column attention
       TRY(run_ln(e, e->x, l.lncw, l.lncb, e->h, M, nullptr, 0));
       if (e->R == 1) return fail("MSA depth 1 is not supported by the column-attention kernel");
       GemmParams qc = gp(M, 3 * d, d, l.c_bqkv, e->qkv, 3 * d);
       qc.q_cols = d; qc.q_scale = 1.0f / sqrtf(static_cast<float>(hd)); qc.rope_cols = 0; qc.head_dim = hd;
       qc.seq_len = e->T;
-      TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->bn_qkv, e->m_h, l.m_cwqkv, qc));
+      TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->g_qkv, e->m_h, l.m_cwqkv, qc));
       {
         ProfScope ps(e, "msa_col_attention");
         AttnParams ap{e->qkv, e->ctx, e->R, 3 * d, d, d, 2 * d, e->T, 1, e->T, static_cast<long long>(e->R) * e->T};
         TRY(launch_attention(ap, e->B * e->T, c.heads, hd, st));
       }
-      TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->bn_o, e->m_ctx, l.m_cwo, gp(M, d, d, l.c_bo, e->x, d)));
+      TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->g_o, e->m_ctx, l.m_cwo, gp(M, d, d, l.c_bo, e->x, d)));
     } else {
       TRY(run_ln(e, e->x, l.ln1w, l.ln1b, e->h, M, nullptr, 0));
       GemmParams q = gp(M, 3 * d, d, l.bqkv, e->qkv, 3 * d);
       q.q_cols = d; q.q_scale = 1.0f / sqrtf(static_cast<float>(hd));
       q.rope_cols = c.arch == PGIBBS_ARCH_ESM2 ? 2 * d : 0;
       q.head_dim = hd; q.seq_len = e->T; q.rope = e->rope;
-      TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->bn_qkv, e->m_h, l.m_wqkv, q));
+      TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->g_qkv, e->m_h, l.m_wqkv, q));
       TRY(run_attention(e));
-      TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->bn_o, e->m_ctx, l.m_wo, gp(M, d, d, l.bo, e->x, d)));
+      TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->g_o, e->m_ctx, l.m_wo, gp(M, d, d, l.bo, e->x, d)));
     }
     TRY(run_ln(e, e->x, l.ln2w, l.ln2b, e->h, M, nullptr, 0));
-    TRY(run_gemm(e, "gemm_fc1", EPI_GELU_F16, e->bn_fc1, e->m_h, l.m_w1, gp(M, F, d, l.b1, e->ffn, F)));
-    TRY(run_gemm(e, "gemm_fc2", EPI_RESID_F32, e->bn_fc2, e->m_ffn, l.m_w2, gp(M, d, F, l.b2, e->x, d)));
+    TRY(run_gemm(e, "gemm_fc1", EPI_GELU_F16, e->g_fc1, e->m_h, l.m_w1, gp(M, F, d, l.b1, e->ffn, F)));
+    TRY(run_gemm(e, "gemm_fc2", EPI_RESID_F32, e->g_fc2, e->m_ffn, l.m_w2, gp(M, d, F, l.b2, e->x, d)));
   }
   // LM head on the scheduled rows only
   const int rows = n_chains * sched.P;
   TRY(run_ln(e, e->x, raw_get(e, "emb_layer_norm_after.weight", -1), raw_get(e, "emb_layer_norm_after.bias", -1),
              e->hs, rows, &sched, iter));
-  TRY(run_gemm(e, "gemm_head", EPI_GELU_F32, e->bn_dense, e->m_hs, e->m_wdense, gp(rows, d, d, e->b_dense, e->g, d)));
+  TRY(run_gemm(e, "gemm_head", EPI_GELU_F32, e->g_dense, e->m_hs, e->m_wdense, gp(rows, d, d, e->b_dense, e->g, d)));
   {
     HeadParams p{};
     p.g = e->g;
@@ -622,6 +657,7 @@ int pgibbs_create(const pgibbs_model_config* cfg, int32_t device_id, pgibbs_engi
   CK(cudaGetDeviceProperties(&prop, device_id));
   if (prop.major != 10) return fail("device %d is sm_%d%d; this engine only runs on sm_100 (B200)", device_id, prop.major, prop.minor);
   g_num_sms = prop.multiProcessorCount;
+  if (const char* f = getenv("PGIBBS_GEMM_CG")) g_force_cg = atoi(f);
   if (cfg->embed_dim % cfg->heads) return fail("embed_dim %% heads != 0");
   if (cfg->embed_dim % 64 || cfg->ffn_dim % 64) return fail("embed_dim and ffn_dim must be multiples of 64");
   if (cfg->embed_dim > kMaxVecPerLane * 128) return fail("embed_dim %d too large (max %d)", cfg->embed_dim, kMaxVecPerLane * 128);
@@ -919,7 +955,8 @@ static int op_device(int device_id) {
 }
 
 int pgibbs_op_gemm(int32_t device_id, const float* A, const float* B, const float* bias, float* C, int32_t M,
-                   int32_t N, int32_t K, int32_t epilogue, int32_t block_n, float* elapsed_ms, int32_t reps) {
+                   int32_t N, int32_t K, int32_t epilogue, int32_t block_n, int32_t cta_group, float* elapsed_ms,
+                   int32_t reps) {
   TRY(op_device(device_id));
   if (epilogue == EPI_QKV_F16) return fail("use the engine for the QKV epilogue");
   const size_t na = static_cast<size_t>(M) * K, nb = static_cast<size_t>(N) * K, nc = static_cast<size_t>(M) * N;
@@ -938,12 +975,14 @@ int pgibbs_op_gemm(int32_t device_id, const float* A, const float* B, const floa
     TRY(to_f16(dA, hA, na, st)); TRY(to_f16(dB, hB, nb, st));
     const bool out16 = epilogue == EPI_BIAS_F16 || epilogue == EPI_GELU_F16;
     if (epilogue == EPI_RESID_F32) CK(cudaMemcpyAsync(dC32, C, nc * sizeof(float), cudaMemcpyDefault, st));
-    const int bn = block_n > 0 ? block_n : pick_block_n(M, N, 16);
+    GemmPlan plan = pick_gemm_plan(M, N, 16);
+    if (block_n > 0) plan.bn = block_n;
+    if (cta_group > 0) plan.cg = cta_group;
     CUtensorMap ma, mb;
     TRY(make_tmap_2d(&ma, hA, M, K, K, kBM));
-    TRY(make_tmap_2d(&mb, hB, N, K, K, bn));
+    TRY(make_tmap_2d(&mb, hB, N, K, K, plan.b_box()));
     GemmParams p = gp(M, N, K, dbias, out16 ? static_cast<void*>(dC16) : static_cast<void*>(dC32), N);
-    TRY(launch_gemm(epilogue, bn, ma, mb, p, st));
+    TRY(launch_gemm(epilogue, plan, ma, mb, p, st));
     CK(cudaStreamSynchronize(st));
     if (out16) {
       f16_to_f32_kernel<<<static_cast<unsigned>((nc + 255) / 256), 256, 0, st>>>(dC16, dC32, nc);
@@ -953,9 +992,9 @@ int pgibbs_op_gemm(int32_t device_id, const float* A, const float* B, const floa
     CK(cudaStreamSynchronize(st));
     if (elapsed_ms && reps > 0) {
       CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-      for (int i = 0; i < 3; ++i) TRY(launch_gemm(epilogue, bn, ma, mb, p, st));
+      for (int i = 0; i < 3; ++i) TRY(launch_gemm(epilogue, plan, ma, mb, p, st));
       CK(cudaEventRecord(e0, st));
-      for (int i = 0; i < reps; ++i) TRY(launch_gemm(epilogue, bn, ma, mb, p, st));
+      for (int i = 0; i < reps; ++i) TRY(launch_gemm(epilogue, plan, ma, mb, p, st));
       CK(cudaEventRecord(e1, st));
       CK(cudaStreamSynchronize(st));
       float ms = 0;

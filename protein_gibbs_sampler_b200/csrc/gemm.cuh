@@ -2,8 +2,12 @@
 //
 //   C[M,N] = epilogue( A[M,K] (fp16, K-major) x B[N,K]^T (fp16, K-major = nn.Linear weight layout) )
 //
-// One CTA per SM, static tile schedule (tile = blockIdx.x + i*gridDim.x, n fastest so the CTAs of a wave
-// share A row-blocks in L2).  Roles:
+// One CTA per SM, static tile schedule (tile = cluster + i*num_clusters, n fastest so the CTAs of a wave
+// share A row-blocks in L2).  CG = 1: one CTA computes a 128 x BN tile.  CG = 2: the two CTAs of a (2,1,1)
+// cluster compute a 256 x BN tile with tcgen05.mma.cta_group::2 -- each CTA stages its own 128 rows of A and
+// BN/2 rows of B, so the operand bytes crossing each SM's shared memory per FLOP are halved (the single-CTA
+// 128 x 256 tile is shared-memory-bandwidth bound: 96 B/clk of UMMA operand reads + 96 B/clk of TMA writes).
+// Roles (per CTA):
 //   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled A/B k-blocks into a kStages smem ring
 //   warp 1      MMA issuer  : one thread issues tcgen05.mma (M=128, N=BN, K=16) into TMEM, fp32 accumulate
 //   warp 2      TMEM allocator (512 columns = two BN-wide accumulator stages)
@@ -45,12 +49,15 @@ constexpr int kBK = 64;  // 64 fp16 = one 128-byte swizzle row
 constexpr int kGemmThreads = 384;
 constexpr int kEpiWarps = 8;
 
-__host__ __device__ constexpr int gemm_stage_bytes(int BN) { return kBM * kBK * 2 + BN * kBK * 2; }
-__host__ __device__ constexpr int gemm_stages(int BN) {
-  int s = (227 * 1024 - 2048) / gemm_stage_bytes(BN);
+// BN = tile width of the CTA (CG=1) or CTA pair (CG=2); each CTA stages BN/CG rows of B per k-block.
+__host__ __device__ constexpr int gemm_stage_bytes(int BN, int CG) { return kBM * kBK * 2 + (BN / CG) * kBK * 2; }
+__host__ __device__ constexpr int gemm_stages(int BN, int CG) {
+  int s = (227 * 1024 - 2048) / gemm_stage_bytes(BN, CG);
   return s > 8 ? 8 : s;
 }
-__host__ __device__ constexpr int gemm_smem_bytes(int BN) { return gemm_stages(BN) * gemm_stage_bytes(BN) + 2048; }
+__host__ __device__ constexpr int gemm_smem_bytes(int BN, int CG) {
+  return gemm_stages(BN, CG) * gemm_stage_bytes(BN, CG) + 2048;
+}
 
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
 
@@ -59,20 +66,151 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// Drain one accumulator tile row-slice: this warp owns TMEM lanes [quad*32, quad*32+32) (= 32 output rows,
+// one per thread) and every second 16-column chunk (`par`).  t_row = TMEM address of the slice's column 0,
+// n0 = first output column of the tile.
 template <int BN, int EPI>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_row, int row, bool row_ok, int n0,
+                                                   int par) {
+  constexpr int kChunks = BN / 16;
+  if constexpr (EPI == EPI_QKV_F16) {
+    // Work unit = 32 columns: two 16-wide chunks that are rotary partners (j, j + head_dim/2).
+    // For head_dim == 16 the partners live inside one chunk; units are then plain 2-chunk groups.
+    const int hd = p.head_dim;
+    const int half = hd >> 1;
+    const int units = BN / 32;
+    for (int u = par; u < units; u += 2) {
+      int c0, c1;  // tile-local column starts of the two chunks
+      if (hd >= 32) {
+        const int per_head = hd / 32;  // units per head
+        const int head = u / per_head, sub = u % per_head;
+        c0 = head * hd + sub * 16;
+        c1 = c0 + half;
+      } else {
+        c0 = u * 32;
+        c1 = c0 + 16;
+      }
+      uint32_t r0[16], r1[16];
+      __syncwarp();
+      tmem_ld16(t_row + c0, r0);
+      tmem_ld16(t_row + c1, r1);
+      tmem_wait_ld();
+      const int g0 = n0 + c0, g1 = n0 + c1;
+      float v0[16], v1[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v0[j] = __uint_as_float(r0[j]) + (g0 + j < p.N ? __ldg(p.bias + g0 + j) : 0.f);
+        v1[j] = __uint_as_float(r1[j]) + (g1 + j < p.N ? __ldg(p.bias + g1 + j) : 0.f);
+      }
+      if (g0 < p.q_cols) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { v0[j] *= p.q_scale; v1[j] *= p.q_scale; }
+      }
+      if (g0 < p.rope_cols && row_ok) {
+        const int t = row % p.seq_len;
+        const float2* cs = p.rope + static_cast<size_t>(t) * half;
+        if (hd >= 32) {
+          const int f0 = (g0 % hd);  // frequency index of v0[0]; partner v1 is f0 + half
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float2 c = __ldg(cs + f0 + j);
+            const float a = v0[j], b = v1[j];
+            v0[j] = a * c.x - b * c.y;  // x*cos + rotate_half(x)*sin, first half: -x2*sin
+            v1[j] = b * c.x + a * c.y;  // second half: +x1*sin
+          }
+        } else {  // head_dim 16: partners (j, j+8) inside each chunk
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float2 c = __ldg(cs + j);
+            float a = v0[j], b = v0[j + 8];
+            v0[j] = a * c.x - b * c.y;
+            v0[j + 8] = b * c.x + a * c.y;
+            a = v1[j]; b = v1[j + 8];
+            v1[j] = a * c.x - b * c.y;
+            v1[j + 8] = b * c.x + a * c.y;
+          }
+        }
+      }
+      if (row_ok) {
+        __half* o = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ldo;
+        if (g0 < p.N) {
+          uint4 w0 = make_uint4(pack_half2(v0[0], v0[1]), pack_half2(v0[2], v0[3]), pack_half2(v0[4], v0[5]),
+                                pack_half2(v0[6], v0[7]));
+          uint4 w1 = make_uint4(pack_half2(v0[8], v0[9]), pack_half2(v0[10], v0[11]),
+                                pack_half2(v0[12], v0[13]), pack_half2(v0[14], v0[15]));
+          *reinterpret_cast<uint4*>(o + g0) = w0;
+          *reinterpret_cast<uint4*>(o + g0 + 8) = w1;
+        }
+        if (g1 < p.N) {
+          uint4 w0 = make_uint4(pack_half2(v1[0], v1[1]), pack_half2(v1[2], v1[3]), pack_half2(v1[4], v1[5]),
+                                pack_half2(v1[6], v1[7]));
+          uint4 w1 = make_uint4(pack_half2(v1[8], v1[9]), pack_half2(v1[10], v1[11]),
+                                pack_half2(v1[12], v1[13]), pack_half2(v1[14], v1[15]));
+          *reinterpret_cast<uint4*>(o + g1) = w0;
+          *reinterpret_cast<uint4*>(o + g1 + 8) = w1;
+        }
+      }
+    }
+  } else {
+    for (int c = par; c < kChunks; c += 2) {
+      uint32_t r[16];
+      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
+      tmem_ld16(t_row + c * 16, r);
+      tmem_wait_ld();
+      const int g = n0 + c * 16;  // N % 16 == 0 -> a chunk is entirely in or out of range
+      if (row_ok && g < p.N) {
+      float v[16];
+#pragma unroll
+      for (int j4 = 0; j4 < 4; ++j4) {
+        float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + g) + j4) : make_float4(0, 0, 0, 0);
+        v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
+        v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
+        v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
+        v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
+      }
+      if constexpr (EPI == EPI_GELU_F16 || EPI == EPI_GELU_F32) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+      }
+      if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_GELU_F16) {
+        __half* o = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ldo + g;
+        *reinterpret_cast<uint4*>(o) = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]),
+                                                  pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
+        *reinterpret_cast<uint4*>(o + 8) = make_uint4(pack_half2(v[8], v[9]), pack_half2(v[10], v[11]),
+                                                      pack_half2(v[12], v[13]), pack_half2(v[14], v[15]));
+      } else {
+        float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + g;
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+          float4 w = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+          if constexpr (EPI == EPI_RESID_F32) {
+            const float4 x = *(reinterpret_cast<const float4*>(o) + j4);
+            w.x += x.x; w.y += x.y; w.z += x.z; w.w += x.w;
+          }
+          *(reinterpret_cast<float4*>(o) + j4) = w;
+        }
+      }
+      }
+    }
+  }
+}
+
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmParams p) {
-  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256, "invalid UMMA N");
-  constexpr int kStages = gemm_stages(BN);
+  static_assert(CG == 1 || CG == 2, "CTA group is 1 or 2");
+  static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256 && (BN / CG) % 8 == 0, "invalid UMMA N");
+  constexpr int kStages = gemm_stages(BN, CG);
+  constexpr int kBNL = BN / CG;                 // rows of B staged by this CTA
   constexpr int kABytes = kBM * kBK * 2;
-  constexpr int kBBytes = BN * kBK * 2;
+  constexpr int kBBytes = kBNL * kBK * 2;
   constexpr int kStageBytes = kABytes + kBBytes;
-  constexpr uint32_t kIdesc = make_idesc_f16(kBM, BN, false, false);
-  constexpr int kChunks = BN / 16;
+  constexpr uint32_t kIdesc = make_idesc_f16(kBM * CG, BN, false, false);
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // 1024-byte alignment is required by the 128B swizzle atoms.
+  // 1024-byte alignment is required by the 128B swizzle atoms.  (Both CTAs of a pair compute the same offset:
+  // the dynamic shared window starts at the same shared::cta address in every CTA of a launch.)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -83,7 +221,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + kBM - 1) / kBM;
+  const int rank = CG == 2 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
+  const int m_tiles = (p.M + kBM * CG - 1) / (kBM * CG);
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = p.K / kBK;
@@ -94,21 +234,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&full_bar[s], 1);   // the leader's producer (arrive.expect_tx for both CTAs' bytes)
+      mbar_init(&empty_bar[s], 1);  // one tcgen05.commit (multicast to both CTAs of a pair)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], kEpiWarps);
+      mbar_init(&tmem_empty[a], kEpiWarps * CG);  // the epilogue warps of both CTAs release the leader's MMA warp
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
+    if constexpr (CG == 2) { tmem_alloc_pair(tmem_slot, 512); tmem_relinquish_pair(); }
+    else { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -117,26 +257,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
         const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        const int a_row = (m_blk * CG + rank) * kBM, b_row = n_blk * BN + rank * kBNL;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = ring + stage * kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-          tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBK, m_blk * kBM);
-          tma_load_2d(sa + kABytes, &tmB, &full_bar[stage], kb * kBK, n_blk * BN);
+          if constexpr (CG == 2) {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * kBK, a_row);
+            tma_load_2d_pair(sa + kABytes, &tmB, &full_bar[stage], kb * kBK, b_row);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBK, a_row);
+            tma_load_2d(sa + kABytes, &tmB, &full_bar[stage], kb * kBK, b_row);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // ---------------------------------------------------------- MMA issuer (leader CTA of a pair only)
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = group; tile < num_tiles; tile += num_groups) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
@@ -149,12 +296,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
             // +32 bytes per UMMA_K slice inside the 128B swizzle row (address field is >>4)
-            umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            if constexpr (CG == 2) umma_f16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);  // frees this smem stage when the MMAs above retire
+          // frees this smem stage (in both CTAs) when the MMAs above retire
+          if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage], 0b11); else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue warps (of both CTAs)
+        if constexpr (CG == 2) umma_commit_pair(&tmem_full[as], 0b11); else umma_commit(&tmem_full[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -165,146 +315,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int par = ew >> 2;    // which alternating 16-column chunks this warp takes
     int as = 0;
     uint32_t aphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const uint32_t leader_empty = CG == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0;
+    for (int tile = group; tile < num_tiles; tile += num_groups) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const int row = m_blk * kBM + quad * 32 + lane;
+      const int row = (m_blk * CG + rank) * kBM + quad * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-
-      if constexpr (EPI == EPI_QKV_F16) {
-        // Work unit = 32 columns: two 16-wide chunks that are rotary partners (j, j + head_dim/2).
-        // For head_dim == 16 the partners live inside one chunk; units are then plain 2-chunk groups.
-        const int hd = p.head_dim;
-        const int half = hd >> 1;
-        const int units = BN / 32;
-        for (int u = par; u < units; u += 2) {
-          int c0, c1;  // tile-local column starts of the two chunks
-          if (hd >= 32) {
-            const int per_head = hd / 32;  // units per head
-            const int head = u / per_head, sub = u % per_head;
-            c0 = head * hd + sub * 16;
-            c1 = c0 + half;
-          } else {
-            c0 = u * 32;
-            c1 = c0 + 16;
-          }
-          uint32_t r0[16], r1[16];
-          __syncwarp();
-          tmem_ld16(t_row + c0, r0);
-          tmem_ld16(t_row + c1, r1);
-          tmem_wait_ld();
-          const int g0 = n_blk * BN + c0, g1 = n_blk * BN + c1;
-          float v0[16], v1[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            v0[j] = __uint_as_float(r0[j]) + (g0 + j < p.N ? __ldg(p.bias + g0 + j) : 0.f);
-            v1[j] = __uint_as_float(r1[j]) + (g1 + j < p.N ? __ldg(p.bias + g1 + j) : 0.f);
-          }
-          if (g0 < p.q_cols) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { v0[j] *= p.q_scale; v1[j] *= p.q_scale; }
-          }
-          if (g0 < p.rope_cols && row_ok) {
-            const int t = row % p.seq_len;
-            const float2* cs = p.rope + static_cast<size_t>(t) * half;
-            if (hd >= 32) {
-              const int f0 = (g0 % hd);  // frequency index of v0[0]; partner v1 is f0 + half
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float2 c = __ldg(cs + f0 + j);
-                const float a = v0[j], b = v1[j];
-                v0[j] = a * c.x - b * c.y;  // x*cos + rotate_half(x)*sin, first half: -x2*sin
-                v1[j] = b * c.x + a * c.y;  // second half: +x1*sin
-              }
-            } else {  // head_dim 16: partners (j, j+8) inside each chunk
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float2 c = __ldg(cs + j);
-                float a = v0[j], b = v0[j + 8];
-                v0[j] = a * c.x - b * c.y;
-                v0[j + 8] = b * c.x + a * c.y;
-                a = v1[j]; b = v1[j + 8];
-                v1[j] = a * c.x - b * c.y;
-                v1[j + 8] = b * c.x + a * c.y;
-              }
-            }
-          }
-          if (row_ok) {
-            __half* o = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ldo;
-            if (g0 < p.N) {
-              uint4 w0 = make_uint4(pack_half2(v0[0], v0[1]), pack_half2(v0[2], v0[3]), pack_half2(v0[4], v0[5]),
-                                    pack_half2(v0[6], v0[7]));
-              uint4 w1 = make_uint4(pack_half2(v0[8], v0[9]), pack_half2(v0[10], v0[11]),
-                                    pack_half2(v0[12], v0[13]), pack_half2(v0[14], v0[15]));
-              *reinterpret_cast<uint4*>(o + g0) = w0;
-              *reinterpret_cast<uint4*>(o + g0 + 8) = w1;
-            }
-            if (g1 < p.N) {
-              uint4 w0 = make_uint4(pack_half2(v1[0], v1[1]), pack_half2(v1[2], v1[3]), pack_half2(v1[4], v1[5]),
-                                    pack_half2(v1[6], v1[7]));
-              uint4 w1 = make_uint4(pack_half2(v1[8], v1[9]), pack_half2(v1[10], v1[11]),
-                                    pack_half2(v1[12], v1[13]), pack_half2(v1[14], v1[15]));
-              *reinterpret_cast<uint4*>(o + g1) = w0;
-              *reinterpret_cast<uint4*>(o + g1 + 8) = w1;
-            }
-          }
-        }
-      } else {
-        for (int c = par; c < kChunks; c += 2) {
-          uint32_t r[16];
-          __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
-          tmem_ld16(t_row + c * 16, r);
-          tmem_wait_ld();
-          const int g = n_blk * BN + c * 16;  // N % 16 == 0 -> a chunk is entirely in or out of range
-          if (row_ok && g < p.N) {
-          float v[16];
-#pragma unroll
-          for (int j4 = 0; j4 < 4; ++j4) {
-            float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + g) + j4) : make_float4(0, 0, 0, 0);
-            v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
-            v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
-            v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
-            v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
-          }
-          if constexpr (EPI == EPI_GELU_F16 || EPI == EPI_GELU_F32) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
-          }
-          if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_GELU_F16) {
-            __half* o = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ldo + g;
-            *reinterpret_cast<uint4*>(o) = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]),
-                                                      pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
-            *reinterpret_cast<uint4*>(o + 8) = make_uint4(pack_half2(v[8], v[9]), pack_half2(v[10], v[11]),
-                                                          pack_half2(v[12], v[13]), pack_half2(v[14], v[15]));
-          } else {
-            float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + g;
-#pragma unroll
-            for (int j4 = 0; j4 < 4; ++j4) {
-              float4 w = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-              if constexpr (EPI == EPI_RESID_F32) {
-                const float4 x = *(reinterpret_cast<const float4*>(o) + j4);
-                w.x += x.x; w.y += x.y; w.z += x.z; w.w += x.w;
-              }
-              *(reinterpret_cast<float4*>(o) + j4) = w;
-            }
-          }
-          }
-        }
-      }
+      gemm_epilogue_tile<BN, EPI>(p, t_row, row, row_ok, n_blk * BN, par);
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_cluster(leader_empty + as * 8);
+        else mbar_arrive(&tmem_empty[as]);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  // A CTA of a pair must outlive every remote access to it (peer MMAs read its smem, commits arrive on its barriers).
+  if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (CG == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 

@@ -162,7 +162,7 @@ class Engine:
 
 
 # ---- stand-alone operators (tests)
-def op_gemm(A, B, bias=None, C=None, epilogue=5, block_n=0, device_id=0, reps=0):
+def op_gemm(A, B, bias=None, C=None, epilogue=5, block_n=0, device_id=0, reps=0, cta_group=0):
     lib = _lib.load()
     A = torch.as_tensor(A, dtype=torch.float32).contiguous()
     B = torch.as_tensor(B, dtype=torch.float32).contiguous()
@@ -172,7 +172,7 @@ def op_gemm(A, B, bias=None, C=None, epilogue=5, block_n=0, device_id=0, reps=0)
     b = None if bias is None else torch.as_tensor(bias, dtype=torch.float32).contiguous()
     ms = ctypes.c_float(0)
     check(lib.pgibbs_op_gemm(device_id, _ptr(A), _ptr(B), None if b is None else _ptr(b), _ptr(out), M, N, K,
-                             epilogue, block_n, ctypes.byref(ms), reps))
+                             epilogue, block_n, cta_group, ctypes.byref(ms), reps))
     return (out, ms.value) if reps else out
 
 
