@@ -106,7 +106,7 @@ int pgibbs_op_gemm(int32_t device_id, const float* A, const float* B, const floa
                    int32_t reps);
 /* attention over fused qkv [n_seq*T, 3*heads*head_dim] (fp32 in, rounded to fp16) -> ctx [n_seq*T, heads*head_dim]. */
 int pgibbs_op_attention(int32_t device_id, const float* qkv, float* ctx, int32_t n_seq, int32_t T, int32_t heads,
-                        int32_t head_dim);
+                        int32_t head_dim, float* elapsed_ms, int32_t reps);
 /* generate_step on given logits rows [rows, vocab] with given Exp(1) noise [rows, n_valid] (NULL: device RNG)
  * -> token ids. */
 int pgibbs_op_sample(int32_t device_id, const float* logits, const float* noise, int32_t rows, int32_t vocab,

@@ -45,7 +45,7 @@ SIGNATURES = {
     "pgibbs_launch_count": (c_i64, [c_void_p]),
     "pgibbs_op_gemm": (c_i32, [c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
                                P(c_f32), c_i32]),
-    "pgibbs_op_attention": (c_i32, [c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32]),
+    "pgibbs_op_attention": (c_i32, [c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, P(c_f32), c_i32]),
     "pgibbs_op_sample": (c_i32, [c_i32, c_void_p, c_void_p, c_i32, c_i32, c_void_p, c_i32, c_i32, c_f32, c_void_p]),
 }
 

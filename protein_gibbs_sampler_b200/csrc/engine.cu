@@ -15,6 +15,7 @@
 
 #include "../../include/pgibbs.h"
 #include "attention.cuh"
+#include "attention_tc.cuh"
 #include "gemm.cuh"
 #include "msa_attention.cuh"
 #include "rowwise.cuh"
@@ -75,6 +76,40 @@ static int make_tmap_2d(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t
   return 0;
 }
 
+// GEMM output [rows, cols] (ld elements between rows), fp16 or fp32: box = 128 bytes x 32 rows, 128B swizzle
+// (one epilogue warp's chunk).
+static int make_tmap_out(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, bool f16) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
+  const uint64_t esz = f16 ? 2 : 4;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / esz), 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                  const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (output) failed with CUresult %d (rows=%llu cols=%llu ld=%llu)",
+                                     (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld);
+  return 0;
+}
+
+// Fused qkv activation viewed as [n_seq][T][3d] fp16 for the tcgen05 attention kernel: box = 64 columns (one head of
+// q, k or v) x 128 tokens of one sequence, 128B swizzle; tokens t >= T are zero-filled (never the next sequence).
+static int make_tmap_qkv3(CUtensorMap* m, const void* ptr, uint64_t n_seq, uint64_t T, uint64_t ld) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t dims[3] = {ld, T, n_seq};
+  cuuint64_t strides[2] = {ld * sizeof(__half), T * ld * sizeof(__half)};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (qkv 3-D) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------- GEMM launch
 static int g_num_sms = 0;
 
@@ -87,6 +122,10 @@ struct GemmPlan {
 
 template <int BN, int EPI, int CG>
 static int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, cudaStream_t st) {
+  if ((reinterpret_cast<uintptr_t>(p.out) & 15) || (p.ldo * (epi_out_f16(EPI) ? 2 : 4)) % 16)
+    return fail("GEMM output must be 16-byte aligned with a 16-byte multiple row pitch");
+  CUtensorMap c;
+  TRY(make_tmap_out(&c, p.out, p.M, p.N, p.ldo, epi_out_f16(EPI)));
   static bool configured = false;
   if (!configured) {
     CK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -105,7 +144,7 @@ static int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const Ge
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG>, a, b, p));
+  CK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG>, a, b, c, p));
   return 0;
 }
 
@@ -132,7 +171,7 @@ static int launch_gemm_bn(GemmPlan g, const CUtensorMap& a, const CUtensorMap& b
 static int launch_gemm(int epi, GemmPlan g, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p,
                        cudaStream_t st) {
   if (p.K % kBK) return fail("GEMM K=%d must be a multiple of %d", p.K, kBK);
-  if (p.N % 16) return fail("GEMM N=%d must be a multiple of 16", p.N);
+  if (p.N % 8) return fail("GEMM N=%d must be a multiple of 8", p.N);
   switch (epi) {
     case EPI_BIAS_F16: return launch_gemm_bn<EPI_BIAS_F16>(g, a, b, p, st);
     case EPI_GELU_F16: return launch_gemm_bn<EPI_GELU_F16>(g, a, b, p, st);
@@ -237,7 +276,7 @@ struct pgibbs_engine {
   float* x = nullptr;
   __half *h = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr, *hs = nullptr;
   float *g = nullptr, *logits = nullptr, *scores = nullptr;
-  CUtensorMap m_h, m_ctx, m_ffn, m_hs;
+  CUtensorMap m_h, m_ctx, m_ffn, m_hs, m_qkv3;
   GemmPlan g_qkv, g_o, g_fc1, g_fc2, g_dense;
   // schedule / rng
   int32_t* positions = nullptr;
@@ -416,6 +455,7 @@ static int ensure_shape(pgibbs_engine* e, int B, int R, int T) {
   TRY(make_tmap_2d(&e->m_ctx, e->ctx, M, d, d, kBM));
   TRY(make_tmap_2d(&e->m_ffn, e->ffn, M, F, F, kBM));
   TRY(make_tmap_2d(&e->m_hs, e->hs, M, d, d, kBM));
+  TRY(make_tmap_qkv3(&e->m_qkv3, e->qkv, static_cast<uint64_t>(B) * R, T, 3 * d));
   const int hd = d / e->cfg.heads;
   e->g_qkv = pick_gemm_plan(e->M, 3 * d, hd >= 64 ? 64 : 32);
   e->g_o = pick_gemm_plan(e->M, d, 16);
@@ -474,10 +514,35 @@ static int launch_attention(const AttnParams& p, int groups, int H, int hd, cuda
   return 0;
 }
 
+// head_dim 64 sequence attention on tcgen05 (everything else keeps the mma.sync kernel above).
+// PGIBBS_ATTN=tc1 selects the first-generation one-tile-per-CTA tcgen05 kernel (correct, latency-bound: kept for
+// A/B measurements), PGIBBS_ATTN=legacy the mma.sync kernel.
+static int g_attn_mode = -1;  // 0 legacy, 1 tc1
+static bool use_tc_attention(int hd) {
+  if (g_attn_mode < 0) {
+    const char* v = getenv("PGIBBS_ATTN");
+    g_attn_mode = (v && !strcmp(v, "tc1")) ? 1 : 0;
+  }
+  return hd == 64 && g_attn_mode == 1;
+}
+static int launch_attention_tc(const CUtensorMap& qkv3, __half* ctx, int n_seq, int T, int H, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    CK(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
+    configured = true;
+  }
+  AttnTcParams p{ctx, T, H * 64, H * 64};
+  dim3 grid((T + 127) / 128, H, n_seq);
+  attention_tcgen05_kernel<<<grid, kAtThreads, kAtSmemBytes, st>>>(qkv3, p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
 static int run_attention(pgibbs_engine* e) {
   const int d = e->cfg.embed_dim, H = e->cfg.heads, hd = d / H;
-  AttnParams p{e->qkv, e->ctx, e->T, 3 * d, d, d, 2 * d, 1, 0, 1, e->T};
   ProfScope ps(e, "attention");
+  if (use_tc_attention(hd)) return launch_attention_tc(e->m_qkv3, e->ctx, e->n_seq, e->T, H, e->stream);
+  AttnParams p{e->qkv, e->ctx, e->T, 3 * d, d, d, 2 * d, 1, 0, 1, e->T};
   return launch_attention(p, e->n_seq, H, hd, e->stream);
 }
 
@@ -1014,7 +1079,7 @@ int pgibbs_op_gemm(int32_t device_id, const float* A, const float* B, const floa
 }
 
 int pgibbs_op_attention(int32_t device_id, const float* qkv, float* ctx, int32_t n_seq, int32_t T, int32_t heads,
-                        int32_t head_dim) {
+                        int32_t head_dim, float* elapsed_ms, int32_t reps) {
   TRY(op_device(device_id));
   const int d = heads * head_dim;
   const size_t nq = static_cast<size_t>(n_seq) * T * 3 * d, nc = static_cast<size_t>(n_seq) * T * d;
@@ -1024,8 +1089,27 @@ int pgibbs_op_attention(int32_t device_id, const float* qkv, float* ctx, int32_t
     TRY(dev_alloc(&d32, nq)); TRY(dev_alloc(&d16, nq)); TRY(dev_alloc(&c32, nc)); TRY(dev_alloc(&c16, nc));
     CK(cudaMemcpy(d32, qkv, nq * sizeof(float), cudaMemcpyDefault));
     TRY(to_f16(d32, d16, nq, nullptr));
-    AttnParams p{d16, c16, T, 3 * d, d, d, 2 * d, 1, 0, 1, T};
-    TRY(launch_attention(p, n_seq, heads, head_dim, nullptr));
+    CUtensorMap m3;
+    if (use_tc_attention(head_dim)) TRY(make_tmap_qkv3(&m3, d16, n_seq, T, 3 * d));
+    auto launch = [&]() -> int {
+      if (use_tc_attention(head_dim)) return launch_attention_tc(m3, c16, n_seq, T, heads, nullptr);
+      AttnParams p{d16, c16, T, 3 * d, d, d, 2 * d, 1, 0, 1, T};
+      return launch_attention(p, n_seq, heads, head_dim, nullptr);
+    };
+    TRY(launch());
+    if (elapsed_ms && reps > 0) {
+      cudaEvent_t e0, e1;
+      CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+      for (int i = 0; i < 3; ++i) TRY(launch());
+      CK(cudaEventRecord(e0, nullptr));
+      for (int i = 0; i < reps; ++i) TRY(launch());
+      CK(cudaEventRecord(e1, nullptr));
+      CK(cudaDeviceSynchronize());
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      *elapsed_ms = ms / reps;
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
     f16_to_f32_kernel<<<static_cast<unsigned>((nc + 255) / 256), 256>>>(c16, c32, nc);
     CK(cudaGetLastError());
     CK(cudaDeviceSynchronize());

@@ -52,153 +52,139 @@ constexpr int kEpiWarps = 8;
 // BN = tile width of the CTA (CG=1) or CTA pair (CG=2); each CTA stages BN/CG rows of B per k-block.
 __host__ __device__ constexpr int gemm_stage_bytes(int BN, int CG) { return kBM * kBK * 2 + (BN / CG) * kBK * 2; }
 __host__ __device__ constexpr int gemm_stages(int BN, int CG) {
-  int s = (227 * 1024 - 2048) / gemm_stage_bytes(BN, CG);
+  int s = (227 * 1024 - 2048 - 8 * 2 * 4096) / gemm_stage_bytes(BN, CG);  // minus barriers/alignment and epilogue staging
   return s > 8 ? 8 : s;
 }
 __host__ __device__ constexpr int gemm_smem_bytes(int BN, int CG) {
-  return gemm_stages(BN, CG) * gemm_stage_bytes(BN, CG) + 2048;
+  return gemm_stages(BN, CG) * gemm_stage_bytes(BN, CG) + 8 * 2 * 4096 + 2048;
 }
 
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)); }
+// erf-GELU, single branch (tools/fit_gelu.py):  e = exp2(|v| P(|v|)) ~= erfc(|v|/sqrt2), |v| clamped to 5.75;
+//   gelu(v) = v > 0 ? v (1 - e/2) : v e/2.   Max abs error 6.2e-7 -- the same as 0.5 v (1 + erff(v/sqrt2)) evaluated
+// in fp32 (6.8e-7) -- at a third of the instructions (the FC1 epilogue is issue-bound otherwise).
+__device__ __forceinline__ float gelu_erf(float v) {
+  const float a = fminf(fabsf(v), 5.75f);
+  float q = 4.278695997e-06f;
+  q = fmaf(q, a, -1.279769367e-05f);
+  q = fmaf(q, a, -5.757883773e-04f);
+  q = fmaf(q, a, 7.670788094e-03f);
+  q = fmaf(q, a, -5.294856802e-02f);
+  q = fmaf(q, a, -4.590439200e-01f);
+  q = fmaf(q, a, -1.151126981e+00f);
+  const float e = exp2f(q * a);
+  return v > 0.f ? v * fmaf(-0.5f, e, 1.0f) : 0.5f * v * e;
+}
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// Drain one accumulator tile row-slice: this warp owns TMEM lanes [quad*32, quad*32+32) (= 32 output rows,
-// one per thread) and every second 16-column chunk (`par`).  t_row = TMEM address of the slice's column 0,
-// n0 = first output column of the tile.
+__host__ __device__ constexpr bool epi_out_f16(int epi) { return epi == EPI_BIAS_F16 || epi == EPI_GELU_F16 || epi == EPI_QKV_F16; }
+constexpr int kEpiStageBytes = 4096;                           // 32 rows x 128 B, one warp's chunk
+constexpr int kEpiStagingTotal = kEpiWarps * 2 * kEpiStageBytes;  // double-buffered per warp
+
+// rotary embedding on one 64-column chunk (chunk start is head-aligned): x*cos + rotate_half(x)*sin
+template <int HD>
+__device__ __forceinline__ void rope_chunk(float (&v)[64], const float2* __restrict__ cs) {
+  constexpr int H = HD / 2;
+#pragma unroll
+  for (int h0 = 0; h0 < 64; h0 += HD) {
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      const float2 c = __ldg(cs + j);
+      const float a = v[h0 + j], b = v[h0 + j + H];
+      v[h0 + j] = a * c.x - b * c.y;      // first half: -x2*sin
+      v[h0 + j + H] = b * c.x + a * c.y;  // second half: +x1*sin
+    }
+  }
+}
+
+// Drain one accumulator tile row-slice.  This warp owns TMEM lanes [quad*32, quad*32+32) (= 32 output rows, one per
+// thread) and every second chunk (`par`) of 128 output bytes per row (64 fp16 / 32 fp32 columns).  Each chunk is
+// staged in this warp's own 128B-swizzled shared-memory buffer and written by one TMA store (or TMA reduce-add
+// for the residual stream), so global writes are full lines, asynchronous, and clipped at the M / N edges.
+//   t_row = TMEM address of the slice's column 0; row0 = first output row of the slice; n0 = first output column.
 template <int BN, int EPI>
-__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_row, int row, bool row_ok, int n0,
-                                                   int par) {
-  constexpr int kChunks = BN / 16;
-  if constexpr (EPI == EPI_QKV_F16) {
-    // Work unit = 32 columns: two 16-wide chunks that are rotary partners (j, j + head_dim/2).
-    // For head_dim == 16 the partners live inside one chunk; units are then plain 2-chunk groups.
-    const int hd = p.head_dim;
-    const int half = hd >> 1;
-    const int units = BN / 32;
-    for (int u = par; u < units; u += 2) {
-      int c0, c1;  // tile-local column starts of the two chunks
-      if (hd >= 32) {
-        const int per_head = hd / 32;  // units per head
-        const int head = u / per_head, sub = u % per_head;
-        c0 = head * hd + sub * 16;
-        c1 = c0 + half;
-      } else {
-        c0 = u * 32;
-        c1 = c0 + 16;
-      }
-      uint32_t r0[16], r1[16];
-      __syncwarp();
-      tmem_ld16(t_row + c0, r0);
-      tmem_ld16(t_row + c1, r1);
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CUtensorMap* tmC, uint32_t t_row,
+                                                   int row0, int lane, int n0, int par, uint8_t* staging, int& sbuf) {
+  constexpr bool kOut16 = epi_out_f16(EPI);
+  constexpr int kCW = kOut16 ? 64 : 32;  // columns per chunk
+  static_assert(BN % kCW == 0, "tile width must be a whole number of epilogue chunks");
+  constexpr int kChunks = BN / kCW;
+  for (int c = par; c < kChunks; c += 2) {
+    const int g = n0 + c * kCW;
+    if (g >= p.N) break;  // warp-uniform: chunk entirely beyond the N edge
+    float v[kCW];
+#pragma unroll
+    for (int hlf = 0; hlf < kCW / 32; ++hlf) {
+      uint32_t r[32];
+      tmem_ld32(t_row + c * kCW + hlf * 32, r);
       tmem_wait_ld();
-      const int g0 = n0 + c0, g1 = n0 + c1;
-      float v0[16], v1[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        v0[j] = __uint_as_float(r0[j]) + (g0 + j < p.N ? __ldg(p.bias + g0 + j) : 0.f);
-        v1[j] = __uint_as_float(r1[j]) + (g1 + j < p.N ? __ldg(p.bias + g1 + j) : 0.f);
-      }
-      if (g0 < p.q_cols) {
+      for (int j = 0; j < 32; ++j) v[hlf * 32 + j] = __uint_as_float(r[j]);
+    }
+    if (p.bias) {
+      if (g + kCW <= p.N) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) { v0[j] *= p.q_scale; v1[j] *= p.q_scale; }
-      }
-      if (g0 < p.rope_cols && row_ok) {
-        const int t = row % p.seq_len;
-        const float2* cs = p.rope + static_cast<size_t>(t) * half;
-        if (hd >= 32) {
-          const int f0 = (g0 % hd);  // frequency index of v0[0]; partner v1 is f0 + half
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float2 c = __ldg(cs + f0 + j);
-            const float a = v0[j], b = v1[j];
-            v0[j] = a * c.x - b * c.y;  // x*cos + rotate_half(x)*sin, first half: -x2*sin
-            v1[j] = b * c.x + a * c.y;  // second half: +x1*sin
-          }
-        } else {  // head_dim 16: partners (j, j+8) inside each chunk
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 c = __ldg(cs + j);
-            float a = v0[j], b = v0[j + 8];
-            v0[j] = a * c.x - b * c.y;
-            v0[j + 8] = b * c.x + a * c.y;
-            a = v1[j]; b = v1[j + 8];
-            v1[j] = a * c.x - b * c.y;
-            v1[j + 8] = b * c.x + a * c.y;
-          }
+        for (int j4 = 0; j4 < kCW / 4; ++j4) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + g) + j4);
+          v[4 * j4 + 0] += b.x; v[4 * j4 + 1] += b.y; v[4 * j4 + 2] += b.z; v[4 * j4 + 3] += b.w;
         }
-      }
-      if (row_ok) {
-        __half* o = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ldo;
-        if (g0 < p.N) {
-          uint4 w0 = make_uint4(pack_half2(v0[0], v0[1]), pack_half2(v0[2], v0[3]), pack_half2(v0[4], v0[5]),
-                                pack_half2(v0[6], v0[7]));
-          uint4 w1 = make_uint4(pack_half2(v0[8], v0[9]), pack_half2(v0[10], v0[11]),
-                                pack_half2(v0[12], v0[13]), pack_half2(v0[14], v0[15]));
-          *reinterpret_cast<uint4*>(o + g0) = w0;
-          *reinterpret_cast<uint4*>(o + g0 + 8) = w1;
-        }
-        if (g1 < p.N) {
-          uint4 w0 = make_uint4(pack_half2(v1[0], v1[1]), pack_half2(v1[2], v1[3]), pack_half2(v1[4], v1[5]),
-                                pack_half2(v1[6], v1[7]));
-          uint4 w1 = make_uint4(pack_half2(v1[8], v1[9]), pack_half2(v1[10], v1[11]),
-                                pack_half2(v1[12], v1[13]), pack_half2(v1[14], v1[15]));
-          *reinterpret_cast<uint4*>(o + g1) = w0;
-          *reinterpret_cast<uint4*>(o + g1 + 8) = w1;
-        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < kCW; ++j) v[j] += (g + j < p.N) ? __ldg(p.bias + g + j) : 0.f;
       }
     }
-  } else {
-    for (int c = par; c < kChunks; c += 2) {
-      uint32_t r[16];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated stores below
-      tmem_ld16(t_row + c * 16, r);
-      tmem_wait_ld();
-      const int g = n0 + c * 16;  // N % 16 == 0 -> a chunk is entirely in or out of range
-      if (row_ok && g < p.N) {
-      float v[16];
+    if constexpr (EPI == EPI_GELU_F16 || EPI == EPI_GELU_F32) {
 #pragma unroll
-      for (int j4 = 0; j4 < 4; ++j4) {
-        float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + g) + j4) : make_float4(0, 0, 0, 0);
-        v[4 * j4 + 0] = __uint_as_float(r[4 * j4 + 0]) + b.x;
-        v[4 * j4 + 1] = __uint_as_float(r[4 * j4 + 1]) + b.y;
-        v[4 * j4 + 2] = __uint_as_float(r[4 * j4 + 2]) + b.z;
-        v[4 * j4 + 3] = __uint_as_float(r[4 * j4 + 3]) + b.w;
-      }
-      if constexpr (EPI == EPI_GELU_F16 || EPI == EPI_GELU_F32) {
+      for (int j = 0; j < kCW; ++j) v[j] = gelu_erf(v[j]);
+    }
+    if constexpr (EPI == EPI_QKV_F16) {
+      if (g < p.q_cols) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+        for (int j = 0; j < kCW; ++j) v[j] *= p.q_scale;
       }
-      if constexpr (EPI == EPI_BIAS_F16 || EPI == EPI_GELU_F16) {
-        __half* o = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ldo + g;
-        *reinterpret_cast<uint4*>(o) = make_uint4(pack_half2(v[0], v[1]), pack_half2(v[2], v[3]),
-                                                  pack_half2(v[4], v[5]), pack_half2(v[6], v[7]));
-        *reinterpret_cast<uint4*>(o + 8) = make_uint4(pack_half2(v[8], v[9]), pack_half2(v[10], v[11]),
-                                                      pack_half2(v[12], v[13]), pack_half2(v[14], v[15]));
-      } else {
-        float* o = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + g;
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-          float4 w = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-          if constexpr (EPI == EPI_RESID_F32) {
-            const float4 x = *(reinterpret_cast<const float4*>(o) + j4);
-            w.x += x.x; w.y += x.y; w.z += x.z; w.w += x.w;
-          }
-          *(reinterpret_cast<float4*>(o) + j4) = w;
-        }
-      }
+      if (g < p.rope_cols) {
+        const int t = (row0 + lane) % p.seq_len;
+        const float2* cs = p.rope + static_cast<size_t>(t) * (p.head_dim >> 1);
+        if (p.head_dim == 64) rope_chunk<64>(v, cs);
+        else if (p.head_dim == 32) rope_chunk<32>(v, cs);
+        else rope_chunk<16>(v, cs);
       }
     }
+    // the TMA store issued from this buffer two chunks ago must have finished reading it
+    if (lane == 0) tma_store_wait_read<1>();
+    __syncwarp();
+    uint8_t* buf = staging + sbuf * kEpiStageBytes;
+    uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      uint4 w;
+      if constexpr (kOut16) {
+        w = make_uint4(pack_half2(v[8 * q], v[8 * q + 1]), pack_half2(v[8 * q + 2], v[8 * q + 3]),
+                       pack_half2(v[8 * q + 4], v[8 * q + 5]), pack_half2(v[8 * q + 6], v[8 * q + 7]));
+      } else {
+        w = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                       __float_as_uint(v[4 * q + 3]));
+      }
+      *reinterpret_cast<uint4*>(rowp + ((q ^ (lane & 7)) << 4)) = w;  // 128B swizzle: conflict-free, matches tmC
+    }
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_2d(tmC, buf, g, row0);
+      else tma_store_2d(tmC, buf, g, row0);
+      tma_store_commit();
+    }
+    sbuf ^= 1;
   }
 }
 
 template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const GemmParams p) {
+                    const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   static_assert(CG == 1 || CG == 2, "CTA group is 1 or 2");
   static_assert(BN % 16 == 0 && BN >= 32 && BN <= 256 && (BN / CG) % 8 == 0, "invalid UMMA N");
   constexpr int kStages = gemm_stages(BN, CG);
@@ -213,7 +199,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   // the dynamic shared window starts at the same shared::cta address in every CTA of a launch.)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint8_t* staging = smem + kStages * kStageBytes;  // epilogue: 8 warps x 2 x 4 KB (1024-aligned)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(staging + kEpiStagingTotal);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full = empty_bar + kStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -231,6 +218,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    prefetch_tmap(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -316,14 +304,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int as = 0;
     uint32_t aphase = 0;
     const uint32_t leader_empty = CG == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0;
+    uint8_t* my_staging = staging + ew * 2 * kEpiStageBytes;
+    int sbuf = 0;
     for (int tile = group; tile < num_tiles; tile += num_groups) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const int row = (m_blk * CG + rank) * kBM + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int row0 = (m_blk * CG + rank) * kBM + quad * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-      gemm_epilogue_tile<BN, EPI>(p, t_row, row, row_ok, n_blk * BN, par);
+      gemm_epilogue_tile<BN, EPI>(p, &tmC, t_row, row0, lane, n_blk * BN, par, my_staging, sbuf);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -332,6 +321,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (lane == 0) tma_store_wait<0>();  // all output tiles of this warp are in global memory
   }
 
   tc_fence_before();

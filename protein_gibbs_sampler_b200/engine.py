@@ -176,12 +176,13 @@ def op_gemm(A, B, bias=None, C=None, epilogue=5, block_n=0, device_id=0, reps=0,
     return (out, ms.value) if reps else out
 
 
-def op_attention(qkv, n_seq, T, heads, head_dim, device_id=0):
+def op_attention(qkv, n_seq, T, heads, head_dim, device_id=0, reps=0):
     lib = _lib.load()
     q = torch.as_tensor(qkv, dtype=torch.float32).contiguous()
     out = torch.empty((n_seq * T, heads * head_dim), dtype=torch.float32)
-    check(lib.pgibbs_op_attention(device_id, _ptr(q), _ptr(out), n_seq, T, heads, head_dim))
-    return out
+    ms = ctypes.c_float(0)
+    check(lib.pgibbs_op_attention(device_id, _ptr(q), _ptr(out), n_seq, T, heads, head_dim, ctypes.byref(ms), reps))
+    return (out, ms.value) if reps else out
 
 
 def op_sample(logits, noise, valid_ids, top_k=0, temperature=None, device_id=0):

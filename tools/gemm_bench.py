@@ -27,6 +27,19 @@ for name, N, K, epi in shapes:
     C0 = torch.randn(M, N) if epi == 2 else None
     if epi == 2:
         want = want + C0
+    # cuBLAS on the same shape, same process / thermal state: the number our kernel is measured against
+    a16, b16 = A.half().cuda(), B.half().cuda()
+    for _ in range(3):
+        a16 @ b16.t()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        a16 @ b16.t()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    print("%-4s N%-5d K%-5d cuBLAS fp16 (no epilogue)  %.3f ms  %7.1f TFLOP/s" % (name, N, K, ms, 2.0 * M * N * K / (ms * 1e-3) / 1e12))
+    del a16, b16
     for cg in (1, 2):
         for bn in (128, 192, 256):
             got, ms = op_gemm(A, B, bias, C=C0, epilogue=epi, block_n=bn, cta_group=cg, reps=20)
