@@ -67,6 +67,7 @@ struct AttnParams {
   int T, ld, ldc, k_off, v_off;
   int inner, inner_stride, row_step;
   long long outer_stride;
+  int q_begin = 0;    // first query row handled by this launch (blockIdx.x counts tiles from here)
 };
 
 constexpr int kAttnBK = 64;   // keys per smem chunk
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(NWARPS * 32) attention_kernel(AttnParams p) {
   __shared__ __align__(16) __half sK[2][kAttnBK * LDS];
   __shared__ __align__(16) __half sV[2][kAttnBK * LDS];
 
-  const int seq = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * kAttnBQ;
+  const int seq = blockIdx.z, head = blockIdx.y, q0 = p.q_begin + blockIdx.x * kAttnBQ;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const long long row0 = (seq / p.inner) * p.outer_stride + static_cast<long long>(seq % p.inner) * p.inner_stride;

@@ -16,6 +16,7 @@
 #include "../../include/pgibbs.h"
 #include "attention.cuh"
 #include "attention_tc.cuh"
+#include "attention_fa.cuh"
 #include "gemm.cuh"
 #include "msa_attention.cuh"
 #include "rowwise.cuh"
@@ -191,7 +192,7 @@ static int g_force_cg = 0;
 static GemmPlan pick_gemm_plan(int M, int N, int multiple_of) {
   static const int cands[] = {256, 192, 128, 64};
   static const double eff1[] = {1.0, 0.95, 0.77, 0.45};   // measured, single CTA (B200, M=16512, K=1280)
-  static const double eff2[] = {1.0, 0.97, 0.90, 0.0};    // CTA pair: operand traffic is no longer the limit
+  static const double eff2[] = {1.08, 1.03, 0.80, 0.0};   // CTA pair, relative to one CTA's 128x256 (same sweep)
   GemmPlan best;
   double best_cost = -1;
   for (int cg = 2; cg >= 1; --cg) {
@@ -202,11 +203,12 @@ static GemmPlan pick_gemm_plan(int M, int N, int multiple_of) {
     for (int i = 0; i < 4; ++i) {
       const int bn = cands[i];
       if (bn % multiple_of) continue;
-      const double eff = (cg == 2 ? eff2[i] : eff1[i]) * (cg == 2 ? 1.3 : 1.0);
+      const double eff = cg == 2 ? eff2[i] : eff1[i];
       if (eff <= 0) continue;
       const long tiles = static_cast<long>(m_tiles) * ((N + bn - 1) / bn);
       const long waves = (tiles + slots - 1) / slots;
-      const double cost = static_cast<double>(waves) * bn * cg / eff;
+      // a wave of CTA pairs (256 x bn per pair) takes as long as a wave of single CTAs (128 x bn each)
+      const double cost = static_cast<double>(waves) * bn / eff;
       if (best_cost < 0 || cost < best_cost) { best_cost = cost; best.bn = bn; best.cg = cg; }
     }
   }
@@ -276,7 +278,7 @@ struct pgibbs_engine {
   float* x = nullptr;
   __half *h = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr, *hs = nullptr;
   float *g = nullptr, *logits = nullptr, *scores = nullptr;
-  CUtensorMap m_h, m_ctx, m_ffn, m_hs, m_qkv3;
+  CUtensorMap m_h, m_ctx, m_ffn, m_hs, m_qkv3, m_ctx3;
   GemmPlan g_qkv, g_o, g_fc1, g_fc2, g_dense;
   // schedule / rng
   int32_t* positions = nullptr;
@@ -456,6 +458,7 @@ static int ensure_shape(pgibbs_engine* e, int B, int R, int T) {
   TRY(make_tmap_2d(&e->m_ffn, e->ffn, M, F, F, kBM));
   TRY(make_tmap_2d(&e->m_hs, e->hs, M, d, d, kBM));
   TRY(make_tmap_qkv3(&e->m_qkv3, e->qkv, static_cast<uint64_t>(B) * R, T, 3 * d));
+  TRY(make_tmap_qkv3(&e->m_ctx3, e->ctx, static_cast<uint64_t>(B) * R, T, d));
   const int hd = d / e->cfg.heads;
   e->g_qkv = pick_gemm_plan(e->M, 3 * d, hd >= 64 ? 64 : 32);
   e->g_o = pick_gemm_plan(e->M, d, 16);
@@ -493,8 +496,12 @@ static int run_gemm(pgibbs_engine* e, const char* name, int epi, GemmPlan g, con
 }
 
 static int launch_attention(const AttnParams& p, int groups, int H, int hd, cudaStream_t st) {
-  if (p.T <= 32) {  // short groups (MSA column attention over R <= 32 rows): 2 warps = 32 queries per CTA
-    dim3 grid((p.T + 31) / 32, H, groups);
+  const int nq = p.T - p.q_begin;  // query rows handled by this launch
+  if (nq <= 16 && hd == 64) {      // a few trailing rows (tail of the tcgen05 kernel): one warp per (group, head)
+    dim3 grid(1, H, groups);
+    attention_kernel<64, 1><<<grid, 32, 0, st>>>(p);
+  } else if (nq <= 32) {  // short groups (MSA column attention over R <= 32 rows): 2 warps = 32 queries per CTA
+    dim3 grid((nq + 31) / 32, H, groups);
     switch (hd) {
       case 16: attention_kernel<16, 2><<<grid, 64, 0, st>>>(p); break;
       case 32: attention_kernel<32, 2><<<grid, 64, 0, st>>>(p); break;
@@ -502,7 +509,7 @@ static int launch_attention(const AttnParams& p, int groups, int H, int hd, cuda
       default: return fail("unsupported head_dim %d (16, 32, 64)", hd);
     }
   } else {
-    dim3 grid((p.T + 63) / 64, H, groups);
+    dim3 grid((nq + 63) / 64, H, groups);
     switch (hd) {
       case 16: attention_kernel<16, 4><<<grid, 128, 0, st>>>(p); break;
       case 32: attention_kernel<32, 4><<<grid, 128, 0, st>>>(p); break;
@@ -514,16 +521,19 @@ static int launch_attention(const AttnParams& p, int groups, int H, int hd, cuda
   return 0;
 }
 
-// head_dim 64 sequence attention on tcgen05 (everything else keeps the mma.sync kernel above).
-// PGIBBS_ATTN=tc1 selects the first-generation one-tile-per-CTA tcgen05 kernel (correct, latency-bound: kept for
-// A/B measurements), PGIBBS_ATTN=legacy the mma.sync kernel.
-static int g_attn_mode = -1;  // 0 legacy, 1 tc1
-static bool use_tc_attention(int hd) {
+// head_dim 64 sequence attention runs on tcgen05 (attention_fa.cuh); everything else keeps the mma.sync kernel.
+// PGIBBS_ATTN=legacy selects the mma.sync kernel, PGIBBS_ATTN=tc1 the first-generation one-tile-per-CTA tcgen05
+// kernel (both kept for A/B measurements).  PGIBBS_ATTN_TAIL=0 makes the tcgen05 kernel also process a nearly
+// empty last query tile itself instead of handing the few trailing rows (T % 128 <= 16) to the mma.sync kernel.
+static int g_attn_mode = -1;  // 0 legacy, 1 tc1, 2 fa
+static int g_attn_tail = 1;
+static int attn_mode(int hd) {
   if (g_attn_mode < 0) {
     const char* v = getenv("PGIBBS_ATTN");
-    g_attn_mode = (v && !strcmp(v, "tc1")) ? 1 : 0;
+    g_attn_mode = (v && !strcmp(v, "tc1")) ? 1 : (v && !strcmp(v, "legacy")) ? 0 : 2;
+    if (const char* t = getenv("PGIBBS_ATTN_TAIL")) g_attn_tail = atoi(t);
   }
-  return hd == 64 && g_attn_mode == 1;
+  return hd == 64 ? g_attn_mode : 0;
 }
 static int launch_attention_tc(const CUtensorMap& qkv3, __half* ctx, int n_seq, int T, int H, cudaStream_t st) {
   static bool configured = false;
@@ -537,11 +547,34 @@ static int launch_attention_tc(const CUtensorMap& qkv3, __half* ctx, int n_seq, 
   CK(cudaGetLastError());
   return 0;
 }
+// qkv: fused activation [n_seq*T, 3*H*64]; ctx: [n_seq*T, H*64].
+static int launch_attention_fa(const CUtensorMap& qkv3, const CUtensorMap& ctx3, const __half* qkv, __half* ctx,
+                               int n_seq, int T, int H, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    CK(cudaFuncSetAttribute(attention_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
+    configured = true;
+  }
+  const int tail = T % 128;
+  const bool split_tail = g_attn_tail && T > 128 && tail > 0 && tail <= 16;
+  AttnFaParams p{T, H, n_seq, split_tail ? T / 128 : (T + 127) / 128};
+  const int n_items = n_seq * H * ((p.n_tiles + 1) / 2);
+  attention_fa_kernel<<<std::min(g_num_sms, n_items), kFaThreads, kFaSmemBytes, st>>>(qkv3, ctx3, p);
+  CK(cudaGetLastError());
+  if (split_tail) {
+    const int d = H * 64;
+    AttnParams tp{qkv, ctx, T, 3 * d, d, d, 2 * d, 1, 0, 1, T, T - tail};
+    TRY(launch_attention(tp, n_seq, H, 64, st));
+  }
+  return 0;
+}
 
 static int run_attention(pgibbs_engine* e) {
   const int d = e->cfg.embed_dim, H = e->cfg.heads, hd = d / H;
   ProfScope ps(e, "attention");
-  if (use_tc_attention(hd)) return launch_attention_tc(e->m_qkv3, e->ctx, e->n_seq, e->T, H, e->stream);
+  const int mode = attn_mode(hd);
+  if (mode == 2) return launch_attention_fa(e->m_qkv3, e->m_ctx3, e->qkv, e->ctx, e->n_seq, e->T, H, e->stream);
+  if (mode == 1) return launch_attention_tc(e->m_qkv3, e->ctx, e->n_seq, e->T, H, e->stream);
   AttnParams p{e->qkv, e->ctx, e->T, 3 * d, d, d, 2 * d, 1, 0, 1, e->T};
   return launch_attention(p, e->n_seq, H, hd, e->stream);
 }
@@ -1089,10 +1122,15 @@ int pgibbs_op_attention(int32_t device_id, const float* qkv, float* ctx, int32_t
     TRY(dev_alloc(&d32, nq)); TRY(dev_alloc(&d16, nq)); TRY(dev_alloc(&c32, nc)); TRY(dev_alloc(&c16, nc));
     CK(cudaMemcpy(d32, qkv, nq * sizeof(float), cudaMemcpyDefault));
     TRY(to_f16(d32, d16, nq, nullptr));
-    CUtensorMap m3;
-    if (use_tc_attention(head_dim)) TRY(make_tmap_qkv3(&m3, d16, n_seq, T, 3 * d));
+    CUtensorMap m3, c3;
+    const int mode = attn_mode(head_dim);
+    if (mode) {
+      TRY(make_tmap_qkv3(&m3, d16, n_seq, T, 3 * d));
+      TRY(make_tmap_qkv3(&c3, c16, n_seq, T, d));
+    }
     auto launch = [&]() -> int {
-      if (use_tc_attention(head_dim)) return launch_attention_tc(m3, c16, n_seq, T, heads, nullptr);
+      if (mode == 2) return launch_attention_fa(m3, c3, d16, c16, n_seq, T, heads, nullptr);
+      if (mode == 1) return launch_attention_tc(m3, c16, n_seq, T, heads, nullptr);
       AttnParams p{d16, c16, T, 3 * d, d, d, 2 * d, 1, 0, 1, T};
       return launch_attention(p, n_seq, heads, head_dim, nullptr);
     };
