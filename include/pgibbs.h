@@ -98,6 +98,10 @@ int pgibbs_profile_read(pgibbs_engine* e, char (*names)[32], float* total_ms, in
 /* Kernels launched by this engine since creation (bench `gpu_launches`). */
 int64_t pgibbs_launch_count(pgibbs_engine* e);
 
+/* Debug: timeline of the tcgen05 attention kernel's CTA 0.  enable != 0 arms it for the following attention launches;
+ * enable == 0 copies 4 x 2048 words of (clock64 << 8 | event code) to `out` (0 = unused slot) and disarms. */
+int pgibbs_debug_attention_trace(uint64_t* out, int32_t enable);
+
 /* Stand-alone operator entry points (unit parity tests; same kernels the engine launches).
  * gemm: C[M,N] = epi(A[M,K] . B[N,K]^T + bias) with fp32 host/device inputs rounded to fp16 operands.
  * epilogue: 0 bias->fp16, 1 gelu->fp16, 2 residual add into C (fp32), 4 gelu->fp32, 5 bias->fp32. */

@@ -43,6 +43,7 @@ SIGNATURES = {
     "pgibbs_profile_enable": (c_i32, [c_void_p, c_i32]),
     "pgibbs_profile_read": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, P(c_i32)]),
     "pgibbs_launch_count": (c_i64, [c_void_p]),
+    "pgibbs_debug_attention_trace": (c_i32, [c_void_p, c_i32]),
     "pgibbs_op_gemm": (c_i32, [c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
                                P(c_f32), c_i32]),
     "pgibbs_op_attention": (c_i32, [c_i32, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_i32, P(c_f32), c_i32]),

@@ -8,18 +8,23 @@
 // Roles (384 threads):
 //   warp 0      TMA producer: Q tiles (double-buffered across items) and 128-key K/V blocks (4-stage ring),
 //               3-D tensor map over the fused qkv activation -- rows t >= T are zero-filled
-//   warp 1      MMA issuer:  S_t = Q_t K_j^T (SS) into TMEM, O_t += P_t V_j (A = P from TMEM, B = V MN-major)
-//   warp 2      TMEM allocator (512 columns: S_A, S_B 128 each; O_A, O_B 80 each)
-//   warps 4-7   softmax of tile A: one thread per query row, S read ONCE from TMEM (two 64-column halves),
+//   warps 1, 3  MMA issuers (tile A, tile B): S_t = Q_t K_j^T (SS) into TMEM, O_t += P_t V_j (A = P from TMEM,
+//               B = V MN-major)
+//   warp 2      TMEM allocator (512 columns: S_A[2], S_B[2] 64 each; O_A, O_B 80 each)
+//   warps 4-7   softmax of tile A: one thread per query row, each S sub-block read ONCE from TMEM,
 //   warps 8-11  softmax of tile B  P = 2^(s - m) written over S as packed fp16; O is rescaled in TMEM only when
-//               the reference maximum m grows by more than 2^8 (lazy rescale: P <= 256 in fp16);
+//               the reference maximum m grows by more than 2^11 (lazy rescale: P <= 2048 in fp16);
 //               final O / l -> fp16 -> swizzled staging (the tile's own Q buffer) -> one TMA store
 // The row sum l is computed by the tensor core: V's MN-major operand is given a second 64-wide panel (LBO) that
 // points at a constant all-ones tile, so PV runs with N = 80 and O[:, 64] = sum_j P_j of the ROUNDED fp16 P --
 // the normalised weights are then an exact convex combination (a stale reference maximum would otherwise leave
 // the rounding error of the dominant P in the output), and the softmax warps need no adds for the sum.
-// Issue order per item: S_A0 S_B0 | PV_A0 S_A1 | PV_B0 S_B1 | PV_A1 S_A2 | ...  tcgen05.mma executes in issue
-// order, so s_full(t, j+1) also tells tile t's softmax warps that PV(t, j) has retired (O is quiescent).
+// Scores are produced in 64-key sub-blocks into a per-tile DOUBLE buffer (S_t[2] x 64 columns): the issuer
+// queues S(t, i+2) right behind PV(t, i), two sub-blocks ahead of the softmax, so a softmax group never waits for
+// the tensor core in steady state and the two groups together keep the MUFU pipe busy.  Issue order per tile:
+//   S_0 S_1 | PV_0 S_2 | PV_1 S_3 | PV_2 S_4 | ...     (one thread's tcgen05.mma execute in issue order)
+// s_full(t, i) therefore implies PV(t, i-2) has retired; the rare O rescale at sub-block i additionally waits
+// for PV(t, i-1) on pv_done[t].
 // Replaces fair-esm MultiheadAttention's bmm / softmax / bmm (call site /root/reference/src/pgen/esm_sampler.py:223).
 #pragma once
 #include <type_traits>
@@ -33,14 +38,19 @@ struct AttnFaParams {
   int H;        // heads (head_dim 64)
   int n_seq;
   int n_tiles;  // 128-row query tiles handled here: ceil(T/128), or floor(T/128) when a tail kernel takes the rest
+  // Optional timeline (debug): CTA 0 appends (clock64 << 8 | event code) words, kFaTraceCap per traced warp
+  // (0: issuer A, 1: softmax warp 4, 2: issuer B, 3: softmax warp 8).  nullptr = off.
+  unsigned long long* trace;
+  int stagger_cycles;  // initial lag of tile B's softmax group behind tile A's (see the softmax role)
 };
+constexpr int kFaTraceCap = 2048;
 
 constexpr int kFaThreads = 384;
 constexpr int kFaKvStages = 4;
 constexpr int kFaTile = 128 * 64 * 2;  // 16 KB: 128 rows x 64 fp16
 constexpr int kFaSmemBytes = kFaTile * (4 + 2 * kFaKvStages + 1) + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int kFaOCols = 80;           // 64 head dims + 16 copies of the row sum
-constexpr float kFaRescaleThreshold = 8.0f;  // log2 units
+constexpr float kFaRescaleThreshold = 11.0f;  // log2 units: P <= 2^11 (fp16 overflows at 2^16)
 
 __device__ __forceinline__ float fa_ex2(float x) {
   float y;
@@ -55,19 +65,6 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                : "memory");
 }
 
-// Multiply the packed-fp16 P columns [0, ncols) of this thread's TMEM lane by alpha (rare slow path).
-__device__ __forceinline__ void fa_rescale_p(uint32_t taddr, float alpha) {
-  uint32_t r[32];
-  tmem_ld32(taddr, r);
-  tmem_wait_ld();
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const float2 f = __half22float2(*reinterpret_cast<__half2*>(&r[i]));
-    __half2 h = __floats2half2_rn(f.x * alpha, f.y * alpha);
-    r[i] = *reinterpret_cast<uint32_t*>(&h);
-  }
-  tmem_st32(taddr, r);
-}
 __device__ __forceinline__ void fa_rescale_o(uint32_t taddr, float alpha) {
 #pragma unroll
   for (int hlf = 0; hlf < 2; ++hlf) {
@@ -99,15 +96,17 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   uint64_t* q_empty = q_full + 2;               // [2]  softmax groups -> producer (count 2)
   uint64_t* kv_full = q_empty + 2;              // [stages]
   uint64_t* kv_empty = kv_full + kFaKvStages;   // [stages] tcgen05.commit
-  uint64_t* s_full = kv_empty + kFaKvStages;    // [2]  per tile: S ready
-  uint64_t* p_ready = s_full + 2;               // [2]  per tile: P written (count 4 = warps)
-  uint64_t* o_full = p_ready + 2;               // [2]  per tile: last PV of the item retired
+  uint64_t* s_full = kv_empty + kFaKvStages;    // [tile 2][buf 2]  S sub-block ready
+  uint64_t* p_ready = s_full + 4;               // [tile 2][buf 2]  P written (count 4 = warps)
+  uint64_t* pv_done = p_ready + 4;              // [2]  per tile: one completion per PV sub-block
+  uint64_t* o_full = pv_done + 2;               // [2]  per tile: last PV of the item retired
   uint64_t* o_free = o_full + 2;                // [2]  per tile: O read out (count 4)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = p.T;
-  const int nkb = (T + 127) >> 7;
+  const int nkb = (T + 127) >> 7;   // 128-key K/V blocks (TMA / smem stage granularity)
+  const int nsub = (T + 63) >> 6;   // 64-key sub-blocks (MMA / softmax granularity)
   const int n_pairs = (p.n_tiles + 1) >> 1;
   const int n_sh = p.n_seq * p.H;
   const int n_items = n_sh * n_pairs;
@@ -119,12 +118,15 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     for (int s = 0; s < 2; ++s) {
       mbar_init(&q_full[s], 1);
       mbar_init(&q_empty[s], 2);
-      mbar_init(&s_full[s], 1);
-      mbar_init(&p_ready[s], 4);
+      mbar_init(&s_full[2 * s], 1);
+      mbar_init(&s_full[2 * s + 1], 1);
+      mbar_init(&p_ready[2 * s], 4);
+      mbar_init(&p_ready[2 * s + 1], 4);
+      mbar_init(&pv_done[s], 1);
       mbar_init(&o_full[s], 1);
       mbar_init(&o_free[s], 4);
     }
-    for (int s = 0; s < kFaKvStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < kFaKvStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }  // both issuers release
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -138,6 +140,13 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+
+  const int trace_slot = warp == 1 ? 0 : warp == 4 ? 1 : warp == 3 ? 2 : warp == 8 ? 3 : -1;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_slot >= 0;
+  int trace_n = 0;
+  auto trace = [&](int code) {
+    if (tracing && trace_n < kFaTraceCap) p.trace[trace_slot * kFaTraceCap + trace_n++] = (static_cast<unsigned long long>(clock64()) << 8) | code;
+  };
 
   // item -> (pair, seq, head): pair-major so that every CTA gets the same mix of full and partial pairs
   auto decode = [&](int item, int& pair, int& seq, int& head) {
@@ -171,70 +180,107 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t kIdescPV = make_idesc_f16(128, kFaOCols, false, true);  // B = [V | ones] is MN-major
-      uint32_t kv_cnt = 0, it = 0;
-      uint32_t p_cnt[2] = {0, 0}, o_cnt[2] = {0, 0};
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        int pair, seq, head;
-        decode(item, pair, seq, head);
-        const int nt = (2 * pair + 1 < p.n_tiles) ? 2 : 1;
-        const int qs = it & 1;
-        mbar_wait(&q_full[qs], (it >> 1) & 1);
-        tc_fence_after();
-        uint64_t qdesc[2];
-        qdesc[0] = make_smem_desc_sw128(smem_u32(sQ + qs * 2 * kFaTile), 1024);
-        qdesc[1] = make_smem_desc_sw128(smem_u32(sQ + qs * 2 * kFaTile + kFaTile), 1024);
-        auto issue_s = [&](int t, int j) {
-          const int st = (kv_cnt + j) % kFaKvStages;
-          const int rem = T - j * 128;
-          const int nk = rem >= 128 ? 128 : ((rem + 15) & ~15);
-          const uint64_t kdesc = make_smem_desc_sw128(smem_u32(sKV + st * 2 * kFaTile), 1024);
-          const uint32_t idesc = make_idesc_f16(128, nk, false, false);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + t * 128, qdesc[t] + 2 * k, kdesc + 2 * k, idesc, k ? 1u : 0u);
-          umma_commit(&s_full[t]);
-        };
-        {
-          const int st = kv_cnt % kFaKvStages;
-          mbar_wait(&kv_full[st], (kv_cnt / kFaKvStages) & 1);
-          tc_fence_after();
-          for (int t = 0; t < nt; ++t) issue_s(t, 0);
-        }
+  } else if (warp == 1 || warp == 3) {
+    // ------------------------------------------------------------------ MMA issuers: warp 1 -> tile A, warp 3 -> tile B
+    // One issuer per tile: the 64-key MMAs are small (32-40 tensor cycles) and cost the issuing warp ~50-100 cycles
+    // each (plus ~100 per commit), so a single issuer serving both tiles in turn was the kernel's critical path.
+    // The whole warp walks the schedule (waits, address arithmetic) so that every operand is warp-uniform and
+    // lives in uniform registers; one elected lane issues the tcgen05 instructions.  (With a `lane == 0` branch
+    // around the loop the compiler wraps EVERY tcgen05.mma in an elect/R2UR waterfall loop, ~10 instructions each.)
+    // Descriptors are built once; per MMA only the low word changes (start address, and for V the LBO that points
+    // at the all-ones panel).
+    const int t = warp >> 1;  // 0 or 1
+    const bool issuer = elect_one();
+    constexpr uint32_t kIdescPV = make_idesc_f16(128, kFaOCols, false, true);  // B = [V | ones] is MN-major
+    constexpr uint32_t kIdescS = make_idesc_f16(128, 64, false, false);
+    const int last_keys = T - (nsub - 1) * 64;                                  // 1..64 valid keys
+    const int last_nk = last_keys >= 64 ? 64 : ((last_keys + 15) & ~15);       // rounded to the UMMA N / K step
+    const uint32_t idesc_s_last = make_idesc_f16(128, last_nk, false, false);
+    const uint64_t kd0 = make_smem_desc_sw128(smem_u32(sKV), 1024);
+    const uint64_t vd0 = make_smem_desc_sw128(smem_u32(sKV + kFaTile), 1024, smem_u32(sOnes) - smem_u32(sKV + kFaTile));
+    const uint32_t desc_hi = static_cast<uint32_t>(kd0 >> 32);                  // same for every descriptor here
+    const uint32_t k_lo0 = static_cast<uint32_t>(kd0), v_lo0 = static_cast<uint32_t>(vd0);
+    const uint32_t q_lo0 = static_cast<uint32_t>(make_smem_desc_sw128(smem_u32(sQ + t * kFaTile), 1024));
+    auto desc = [&](uint32_t lo) { return (static_cast<uint64_t>(desc_hi) << 32) | lo; };
+    const uint32_t tS0 = tmem_base + t * 128, tO = tmem_base + 256 + t * kFaOCols;
+    uint32_t kv_cnt = 0, it = 0;
+    uint32_t p_par = 0, o_par = 0;  // phase parities: bit b of p_ready[t][b], o_free[t] (waits done so far)
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it, kv_cnt += nkb) {
+      const int pair = item / n_sh;
+      if (2 * pair + t >= p.n_tiles) {
+        // No tile for this issuer in this item: it still owes kv_empty its arrival for every K/V block (paced by
+        // kv_full, so that the arrival lands in the right phase of the ring).
         for (int j = 0; j < nkb; ++j) {
-          const int st = (kv_cnt + j) % kFaKvStages;
-          const int rem = T - j * 128;
-          const int nk = rem >= 128 ? 128 : ((rem + 15) & ~15);
-          // V_j: rows = keys (the MMA's K), 64 contiguous head-dim values per row (the MMA's N): MN-major, 128B
-          // swizzle; a K=16 step is two 8-row swizzle atoms = 2048 B.
-          // LBO = distance to the next 64-wide N panel = the all-ones tile (columns 64..79 of the operand).
-          const uint32_t sv = smem_u32(sKV + st * 2 * kFaTile + kFaTile);
-          const uint64_t vdesc = make_smem_desc_sw128(sv, 1024, smem_u32(sOnes) - sv);
-          for (int t = 0; t < nt; ++t) {
-            mbar_wait(&p_ready[t], p_cnt[t] & 1);
-            ++p_cnt[t];
-            if (j == 0) mbar_wait(&o_free[t], (o_cnt[t] & 1) ^ 1);  // previous item's O has been read out
-            tc_fence_after();
-            const uint32_t tS = tmem_base + t * 128, tO = tmem_base + 256 + t * kFaOCols;
-            for (int k = 0; k < nk / 16; ++k)
-              umma_f16_ts(tO, tS + 8 * k, vdesc + static_cast<uint64_t>(k) * (2048 >> 4), kIdescPV, (j | k) ? 1u : 0u);
-            if (j + 1 < nkb) {
-              if (t == 0) {
-                const uint32_t c = kv_cnt + j + 1;
-                mbar_wait(&kv_full[c % kFaKvStages], (c / kFaKvStages) & 1);
-                tc_fence_after();
-              }
-              issue_s(t, j + 1);
-            } else {
-              umma_commit(&o_full[t]);
-              ++o_cnt[t];
-            }
-          }
-          umma_commit(&kv_empty[st]);  // K_j / V_j fully consumed once everything issued so far retires
+          const uint32_t c = kv_cnt + j;
+          mbar_wait(&kv_full[c % kFaKvStages], (c / kFaKvStages) & 1);
+          if (issuer) mbar_arrive(&kv_empty[c % kFaKvStages]);
+          __syncwarp();
         }
-        kv_cnt += nkb;
+        continue;
+      }
+      const int qs = it & 1;
+      trace(0x01);  // item begins (issuer)
+      mbar_wait(&q_full[qs], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t q_lo = q_lo0 + qs * (2 * kFaTile >> 4);
+      // S(i) = Q K_i^T into buffer i & 1.  K rows of sub-block i: stage of block i/2, +8 KB for the odd half.
+      auto issue_s = [&](int i) {
+        const uint32_t delta = ((kv_cnt + (i >> 1)) % kFaKvStages) * (2 * kFaTile >> 4) + (i & 1) * (kFaTile >> 5);
+        const uint32_t kd = k_lo0 + delta;
+        const uint32_t idesc = (i + 1 == nsub) ? idesc_s_last : kIdescS;
+        const uint32_t tS = tS0 + (i & 1) * 64;
+        if (issuer) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_ss(tS, desc(q_lo + 2 * k), desc(kd + 2 * k), idesc, k ? 1u : 0u);
+          umma_commit(&s_full[2 * t + (i & 1)]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(&kv_full[kv_cnt % kFaKvStages], (kv_cnt / kFaKvStages) & 1);
+      tc_fence_after();
+      issue_s(0);
+      if (nsub > 1) issue_s(1);
+      for (int i = 0; i < nsub; ++i) {
+        const int b = i & 1;
+        const int st = (kv_cnt + (i >> 1)) % kFaKvStages;
+        const int ksteps = (i + 1 == nsub) ? last_nk >> 4 : 4;
+        // V rows of sub-block i: keys are the MMA's K, 64 contiguous head-dim values per key row (the MMA's N):
+        // MN-major, 128B swizzle; a K=16 step is two 8-row swizzle atoms = 2048 B.  The LBO field (bits 16..29)
+        // is the distance to the next 64-wide N panel = the all-ones tile (columns 64..79 of the operand), so
+        // moving the start address by `delta` moves the LBO by -delta.
+        const uint32_t delta = st * (2 * kFaTile >> 4) + b * (kFaTile >> 5);
+        const uint32_t vd = v_lo0 + delta - (delta << 16);
+        mbar_wait(&p_ready[2 * t + b], (p_par >> b) & 1);
+        p_par ^= 1u << b;
+        trace(0x10 + t);  // P(i) seen
+        if (i == 0) mbar_wait(&o_free[t], (o_par & 1) ^ 1);  // previous item's O has been read out
+        tc_fence_after();
+        trace(0x30);  // fences done
+        if (issuer) {
+          for (int k = 0; k < ksteps; ++k)
+            umma_f16_ts(tO, tS0 + b * 64 + 8 * k, desc(vd + k * (2048 >> 4)), kIdescPV, (i | k) ? 1u : 0u);
+        }
+        __syncwarp();
+        trace(0x31);  // PV MMAs issued
+        if (issuer) umma_commit(&pv_done[t]);
+        __syncwarp();
+        trace(0x32);  // pv_done commit issued
+        if (i + 2 < nsub) {
+          if (b == 0) {  // sub-block i+2 opens the next 128-key block
+            const uint32_t c = kv_cnt + (i >> 1) + 1;
+            mbar_wait(&kv_full[c % kFaKvStages], (c / kFaKvStages) & 1);
+            tc_fence_after();
+          }
+          issue_s(i + 2);
+        }
+        if (i + 1 == nsub) {
+          if (issuer) umma_commit(&o_full[t]);
+          o_par ^= 1u;
+        }
+        // this tile is done with K/V block i/2 (kv_empty counts both issuers) once everything issued so far retires
+        if ((b || i + 1 == nsub) && issuer) umma_commit(&kv_empty[st]);
+        __syncwarp();
+        trace(0x18 + t);  // PV(i) [+ S(i+2)] issued
       }
     }
   } else if (warp >= 4) {
@@ -245,7 +291,27 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
     const uint32_t tS = tmem_base + t * 128 + lane_off, tO = tmem_base + 256 + t * kFaOCols + lane_off;
     const bool leader = (threadIdx.x & 127) == 0;
     constexpr float kLog2e = 1.4426950408889634f;
-    uint32_t s_cnt = 0, o_cnt = 0, it = 0;
+    uint32_t s_par = 0, o_cnt = 0, pv_cnt = 0, it = 0;
+    // The leader hands a Q/O staging buffer back to the producer once the TMA store has finished READING it.
+    // Waiting for that right after issuing the store would stall the leader's warp ~1000 cycles per item (and the
+    // whole group with it, through p_ready); it is done one sub-block into the next item instead, when it is free.
+    // The two groups share each SM sub-partition's MUFU pipe.  A sub-block is ~650 cycles of non-MUFU work (TMEM
+    // load, row maximum, TMEM store, hand-over) followed by ~512 cycles of ex2; started together, both groups sit
+    // in the same phase and a sub-block pair costs 650 + 2*512 cycles, started half a period apart one group's ex2
+    // phase hides the other's overhead (650 + 512).  The lag is neutral-stable (both groups do identical work), so
+    // it is set once here.
+    if (t == 1 && p.stagger_cycles > 0) {
+      const long long t0 = clock64();
+      while (clock64() - t0 < p.stagger_cycles) { }
+    }
+    int pending_qs = -1;
+    auto release_stage = [&]() {
+      if (pending_qs >= 0) {
+        tma_store_wait_read<0>();
+        mbar_arrive(&q_empty[pending_qs]);
+        pending_qs = -1;
+      }
+    };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       int pair, seq, head;
       decode(item, pair, seq, head);
@@ -253,6 +319,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       const int tile = 2 * pair + t;
       if (tile >= p.n_tiles) {  // no second tile in this item: only keep the Q-stage handshake going
         if (leader) {
+          release_stage();
           // paced by the producer (q_full of THIS item), or two early arrivals could complete one phase
           mbar_wait(&q_full[qs], (it >> 1) & 1);
           mbar_arrive(&q_empty[qs]);
@@ -261,64 +328,71 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       }
       const bool warp_live = tile * 128 + quad * 32 < T;  // warp-uniform: any valid query row in this warp
       float m_used = -INFINITY;                           // reference maximum (log2 domain)
-      for (int j = 0; j < nkb; ++j) {
-        mbar_wait(&s_full[t], s_cnt & 1);
-        ++s_cnt;
+      for (int i = 0; i < nsub; ++i) {
+        const int b = i & 1;
+        trace(0x20);  // waiting for S(i)
+        mbar_wait(&s_full[2 * t + b], (s_par >> b) & 1);
+        s_par ^= 1u << b;
         tc_fence_after();
+        trace(0x21);  // S(i) ready
         if (warp_live) {
-          const int rem = T - j * 128;                    // valid keys in this block (>= 1)
-          const int nk = rem >= 128 ? 128 : ((rem + 15) & ~15);
-          // `W` consecutive score columns starting at `c0` (a multiple of 64): reference update, P = 2^(s - m)
-          auto chunk = [&](auto wtag, int c0) {
+          const int rem = T - i * 64;                     // valid keys in this sub-block (>= 1)
+          const uint32_t tSb = tS + b * 64;
+          // `W` score columns: reference update (lazy), P = 2^(s - m) as packed fp16 over the consumed scores
+          auto chunk = [&](auto wtag) {
             constexpr int W = decltype(wtag)::value;
             float v[W];
 #pragma unroll
             for (int g = 0; g < W / 32; ++g) {
               uint32_t r[32];
-              tmem_ld32(tS + c0 + g * 32, r);
+              tmem_ld32(tSb + g * 32, r);
               tmem_wait_ld();
 #pragma unroll
-              for (int i = 0; i < 32; ++i) v[g * 32 + i] = __uint_as_float(r[i]);
+              for (int c = 0; c < 32; ++c) v[g * 32 + c] = __uint_as_float(r[c]);
             }
-            if (rem < c0 + W) {                           // block edge: keys >= T do not exist
+            if (rem < W) {                                // sequence edge: keys >= T do not exist
 #pragma unroll
-              for (int i = 0; i < W; ++i)
-                if (c0 + i >= rem) v[i] = -INFINITY;
+              for (int c = 0; c < W; ++c)
+                if (c >= rem) v[c] = -INFINITY;
             }
-            float mx = v[0];
+            float mx4[4] = {v[0], v[1], v[2], v[3]};
 #pragma unroll
-            for (int i = 1; i < W; ++i) mx = fmaxf(mx, v[i]);
-            mx *= kLog2e;
+            for (int c = 4; c < W; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], v[c]);
+            const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * kLog2e;
             if (__any_sync(0xffffffffu, mx > m_used + kFaRescaleThreshold)) {
               const float m_new = fmaxf(m_used, mx);
-              const float alpha = fa_ex2(m_used - m_new);  // 0 on the very first chunk (m_used = -inf)
-              if (j > 0) fa_rescale_o(tO, alpha);           // PV(t, j-1) has retired (see header)
-              if (c0 > 0) fa_rescale_p(tS, alpha);          // first half of this block used the old reference
-              if (j > 0 || c0 > 0) tmem_wait_st();
+              if (i > 0) {
+                // O is quiescent once PV(t, i-1) -- completion number pv_cnt + i of pv_done[t] -- has retired
+                mbar_wait(&pv_done[t], (pv_cnt + i - 1) & 1);
+                tc_fence_after();
+                fa_rescale_o(tO, fa_ex2(m_used - m_new));
+                tmem_wait_st();
+              }
               m_used = m_new;
             }
             uint32_t pk[W / 2];
 #pragma unroll
-            for (int i = 0; i < W; i += 2) {
-              __half2 h = __floats2half2_rn(fa_ex2(fmaf(v[i], kLog2e, -m_used)), fa_ex2(fmaf(v[i + 1], kLog2e, -m_used)));
-              pk[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+            for (int c = 0; c < W; c += 2) {
+              __half2 h = __floats2half2_rn(fa_ex2(fmaf(v[c], kLog2e, -m_used)), fa_ex2(fmaf(v[c + 1], kLog2e, -m_used)));
+              pk[c >> 1] = *reinterpret_cast<uint32_t*>(&h);
             }
-            // P (fp16 x2 per column) over the consumed part of S
-            if constexpr (W == 64) tmem_st32(tS + (c0 >> 1), pk); else tmem_st16(tS + (c0 >> 1), pk);
+            if constexpr (W == 64) tmem_st32(tSb, pk); else tmem_st16(tSb, pk);
           };
-          if (nk > 32) chunk(std::integral_constant<int, 64>{}, 0); else chunk(std::integral_constant<int, 32>{}, 0);
-          if (nk > 96) chunk(std::integral_constant<int, 64>{}, 64);
-          else if (nk > 64) chunk(std::integral_constant<int, 32>{}, 64);
+          if (rem > 32) chunk(std::integral_constant<int, 64>{}); else chunk(std::integral_constant<int, 32>{});
           tmem_wait_st();
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_ready[t]);
+        if (lane == 0) mbar_arrive(&p_ready[2 * t + b]);
+        trace(0x22);  // P(i) handed over
+        if (leader && i == 0) release_stage();
       }
+      pv_cnt += nsub;
       // ---- output: O / l -> fp16 -> staging (this tile's Q buffer: every S MMA of the item has retired) -> TMA store
       mbar_wait(&o_full[t], o_cnt & 1);
       ++o_cnt;
       tc_fence_after();
+      trace(0x23);  // O complete
       uint8_t* stage = sQ + (qs * 2 + t) * kFaTile;
       if (warp_live) {
         float inv;
@@ -352,15 +426,20 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[t]);
       fence_proxy_async();            // generic-proxy smem writes -> visible to the TMA (async proxy)
+      trace(0x24);  // O staged
       fa_bar_sync(1 + t, 128);
+      trace(0x25);  // group barrier passed
       if (leader) {
+        release_stage();  // (only when the item had a single sub-block)
         tma_store_3d(&tmCtx, stage, head * 64, tile * 128, seq);  // rows >= T are clipped by the tensor map
         tma_store_commit();
-        tma_store_wait_read<0>();
-        mbar_arrive(&q_empty[qs]);
+        pending_qs = qs;  // released during the next item (see release_stage)
       }
     }
-    if (leader) tma_store_wait<0>();
+    if (leader) {
+      release_stage();
+      tma_store_wait<0>();
+    }
   }
 
   tc_fence_before();

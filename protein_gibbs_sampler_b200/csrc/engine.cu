@@ -484,7 +484,12 @@ static int run_ln(pgibbs_engine* e, const float* x, const float* w, const float*
   if (gather) p.sched = *gather; else p.sched.positions = nullptr;
   p.iter = iter; p.T = e->T;
   ProfScope ps(e, "layernorm");
-  layernorm_kernel<true><<<(rows + 7) / 8, 256, 0, e->stream>>>(p);
+  const dim3 grid((rows + 7) / 8);
+  const int vpl = (p.d / 4 + 31) / 32;  // float4 vectors per lane
+  if (vpl <= 3) layernorm_kernel<true, 3><<<grid, 256, 0, e->stream>>>(p);
+  else if (vpl <= 6) layernorm_kernel<true, 6><<<grid, 256, 0, e->stream>>>(p);
+  else if (vpl <= 10) layernorm_kernel<true, 10><<<grid, 256, 0, e->stream>>>(p);
+  else layernorm_kernel<true, kMaxVecPerLane><<<grid, 256, 0, e->stream>>>(p);
   CK(cudaGetLastError());
   return 0;
 }
@@ -525,13 +530,16 @@ static int launch_attention(const AttnParams& p, int groups, int H, int hd, cuda
 // PGIBBS_ATTN=legacy selects the mma.sync kernel, PGIBBS_ATTN=tc1 the first-generation one-tile-per-CTA tcgen05
 // kernel (both kept for A/B measurements).  PGIBBS_ATTN_TAIL=0 makes the tcgen05 kernel also process a nearly
 // empty last query tile itself instead of handing the few trailing rows (T % 128 <= 16) to the mma.sync kernel.
+static unsigned long long* g_fa_trace = nullptr;  // device buffer for the attention timeline (debug)
 static int g_attn_mode = -1;  // 0 legacy, 1 tc1, 2 fa
 static int g_attn_tail = 1;
+static int g_attn_stagger = 600;  // PGIBBS_ATTN_STAGGER (cycles)
 static int attn_mode(int hd) {
   if (g_attn_mode < 0) {
     const char* v = getenv("PGIBBS_ATTN");
     g_attn_mode = (v && !strcmp(v, "tc1")) ? 1 : (v && !strcmp(v, "legacy")) ? 0 : 2;
     if (const char* t = getenv("PGIBBS_ATTN_TAIL")) g_attn_tail = atoi(t);
+    if (const char* t = getenv("PGIBBS_ATTN_STAGGER")) g_attn_stagger = atoi(t);
   }
   return hd == 64 ? g_attn_mode : 0;
 }
@@ -557,7 +565,7 @@ static int launch_attention_fa(const CUtensorMap& qkv3, const CUtensorMap& ctx3,
   }
   const int tail = T % 128;
   const bool split_tail = g_attn_tail && T > 128 && tail > 0 && tail <= 16;
-  AttnFaParams p{T, H, n_seq, split_tail ? T / 128 : (T + 127) / 128};
+  AttnFaParams p{T, H, n_seq, split_tail ? T / 128 : (T + 127) / 128, g_fa_trace, g_attn_stagger};
   const int n_items = n_seq * H * ((p.n_tiles + 1) / 2);
   attention_fa_kernel<<<std::min(g_num_sms, n_items), kFaThreads, kFaSmemBytes, st>>>(qkv3, ctx3, p);
   CK(cudaGetLastError());
@@ -1038,6 +1046,20 @@ int pgibbs_profile_read(pgibbs_engine* e, char (*names)[32], float* total_ms, in
 }
 
 int64_t pgibbs_launch_count(pgibbs_engine* e) { return e ? e->launches : 0; }
+
+int pgibbs_debug_attention_trace(uint64_t* out, int32_t enable) {
+  if (enable) {
+    if (!g_fa_trace) CK(cudaMalloc(&g_fa_trace, 4 * kFaTraceCap * sizeof(unsigned long long)));
+    CK(cudaMemset(g_fa_trace, 0, 4 * kFaTraceCap * sizeof(unsigned long long)));
+    return 0;
+  }
+  if (!g_fa_trace) return fail("attention trace was not enabled");
+  CK(cudaDeviceSynchronize());
+  if (out) CK(cudaMemcpy(out, g_fa_trace, 4 * kFaTraceCap * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  CK(cudaFree(g_fa_trace));
+  g_fa_trace = nullptr;
+  return 0;
+}
 
 // ------------------------------------------------------------------------ stand-alone operator entry points
 static int op_device(int device_id) {

@@ -240,17 +240,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // Producer and MMA warps: the WHOLE warp walks the tile schedule (barrier waits, address arithmetic) and one
+  // elected lane issues the TMA / tcgen05 instructions.  Under a `lane == 0` branch the operands are per-thread
+  // values and the compiler wraps every UTCHMMA / UTMALDG in an elect + R2UR waterfall loop (~12 instructions);
+  // executed warp-uniformly they live in uniform registers and the instructions issue back to back.
   if (warp == 0) {
     // ------------------------------------------------------------ producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = group; tile < num_tiles; tile += num_groups) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        const int a_row = (m_blk * CG + rank) * kBM, b_row = n_blk * BN + rank * kBNL;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = ring + stage * kStageBytes;
+    const bool issuer = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = group; tile < num_tiles; tile += num_groups) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int a_row = (m_blk * CG + rank) * kBM, b_row = n_blk * BN + rank * kBNL;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = ring + stage * kStageBytes;
+        if (issuer) {
           if constexpr (CG == 2) {
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
             tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * kBK, a_row);
@@ -260,17 +265,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBK, a_row);
             tma_load_2d(sa + kABytes, &tmB, &full_bar[stage], kb * kBK, b_row);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------- MMA issuer (leader CTA of a pair only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
+      const uint32_t desc_hi = static_cast<uint32_t>(make_smem_desc_sw128(0, 1024) >> 32);
       for (int tile = group; tile < num_tiles; tile += num_groups) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
@@ -279,20 +287,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + stage * kStageBytes);
-          const uint64_t adesc = make_smem_desc_sw128(sa, 1024);
-          const uint64_t bdesc = make_smem_desc_sw128(sa + kABytes, 1024);
+          const uint32_t a_lo = static_cast<uint32_t>(make_smem_desc_sw128(sa, 1024));
+          const uint32_t b_lo = static_cast<uint32_t>(make_smem_desc_sw128(sa + kABytes, 1024));
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // +32 bytes per UMMA_K slice inside the 128B swizzle row (address field is >>4)
-            if constexpr (CG == 2) umma_f16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_f16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; ++k) {
+              // +32 bytes per UMMA_K slice inside the 128B swizzle row (address field is >>4)
+              const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k);
+              const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k);
+              if constexpr (CG == 2) umma_f16_ss_pair(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_f16_ss(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            // frees this smem stage (in both CTAs) when the MMAs above retire
+            if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage], 0b11); else umma_commit(&empty_bar[stage]);
           }
-          // frees this smem stage (in both CTAs) when the MMAs above retire
-          if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage], 0b11); else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         // accumulator ready for the epilogue warps (of both CTAs)
-        if constexpr (CG == 2) umma_commit_pair(&tmem_full[as], 0b11); else umma_commit(&tmem_full[as]);
+        if (issuer) {
+          if constexpr (CG == 2) umma_commit_pair(&tmem_full[as], 0b11); else umma_commit(&tmem_full[as]);
+        }
+        __syncwarp();
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
