@@ -59,9 +59,11 @@ __host__ __device__ constexpr int gemm_smem_bytes(int BN, int CG) {
   return gemm_stages(BN, CG) * gemm_stage_bytes(BN, CG) + 8 * 2 * 4096 + 2048;
 }
 
-// erf-GELU, single branch (tools/fit_gelu.py):  e = exp2(|v| P(|v|)) ~= erfc(|v|/sqrt2), |v| clamped to 5.75;
-//   gelu(v) = v > 0 ? v (1 - e/2) : v e/2.   Max abs error 6.2e-7 -- the same as 0.5 v (1 + erff(v/sqrt2)) evaluated
-// in fp32 (6.8e-7) -- at a third of the instructions (the FC1 epilogue is issue-bound otherwise).
+// erf-GELU without a branch (tools/fit_gelu.py):  e = exp2(a P(a)) ~= erfc(a / sqrt2) with a = min(|v|, 5.75), and
+//   gelu(v) = v Phi(v) = relu(v) - |v| e / 2        (v > 0: v (1 - e/2);  v <= 0: v e/2).
+// Max abs error 6.2e-7 -- the same as 0.5 v (1 + erff(v/sqrt2)) evaluated in fp32 (6.8e-7).  12 instructions per
+// element (|v| is a free operand modifier, ex2.approx.ftz needs no range fix-up: e <= 1 and a flushed e only
+// matters where |v| e / 2 < 1e-37); the FC1 epilogue competes with the MMA / TMA issue warps for issue slots.
 __device__ __forceinline__ float gelu_erf(float v) {
   const float a = fminf(fabsf(v), 5.75f);
   float q = 4.278695997e-06f;
@@ -71,8 +73,9 @@ __device__ __forceinline__ float gelu_erf(float v) {
   q = fmaf(q, a, -5.294856802e-02f);
   q = fmaf(q, a, -4.590439200e-01f);
   q = fmaf(q, a, -1.151126981e+00f);
-  const float e = exp2f(q * a);
-  return v > 0.f ? v * fmaf(-0.5f, e, 1.0f) : 0.5f * v * e;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q * a));
+  return fmaf(-0.5f * fabsf(v), e, fmaxf(v, 0.f));
 }
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {

@@ -123,6 +123,7 @@ def _tokens(cfg, shape, seed):
     ("roberta_large", 33, 1280, 20, 5120, (2, 66)),         # full-depth ESM-1b (config 2/5 model)
     ("esm2", 33, 1280, 20, 5120, (2, 40)),                  # full-depth ESM-2 650M (config 4 model)
     ("msa_transformer", 2, 128, 2, 256, (2, 4, 17)), ("msa_transformer", 2, 768, 12, 3072, (1, 8, 33)),
+    ("msa_transformer", 2, 128, 2, 256, (2, 1, 9)),         # single-row MSA (pgen_msa_revised --alignment_size 1)
     ("msa_transformer", 12, 768, 12, 3072, (1, 6, 40)),     # full-depth MSA-1b (config 3 model)
 ])
 def test_forward_logits_vs_oracle(arch, layers, d, H, F, shape):
