@@ -10,7 +10,11 @@
 //               3-D tensor map over the fused qkv activation -- rows t >= T are zero-filled
 //   warps 1, 3  MMA issuers (tile A, tile B): S_t = Q_t K_j^T (SS) into TMEM, O_t += P_t V_j (A = P from TMEM,
 //               B = V MN-major)
-//   warp 2      TMEM allocator (512 columns: S_A[2], S_B[2] 64 each; O_A, O_B 80 each)
+//   warp 2      TMEM allocator (512 columns: S_A[2], S_B[2] 64 each; O_A, O_B 80 each); also the TAIL warp: when
+//               T = 128 k + r with 1 <= r <= 8 (T = L + 2 for the usual L) the r trailing query rows would cost a
+//               whole 128-row tile (or a second kernel that re-reads every K/V row from HBM); instead this warp
+//               computes them with mma.sync straight from the K/V blocks of the ring, transposed (keys are the MMA
+//               M dimension, the <= 8 queries its N = 8), once per (sequence, head)
 //   warps 4-7   softmax of tile A: one thread per query row, each S sub-block read ONCE from TMEM,
 //   warps 8-11  softmax of tile B  P = 2^(s - m) written over S as packed fp16; O is rescaled in TMEM only when
 //               the reference maximum m grows by more than 2^11 (lazy rescale: P <= 2048 in fp16);
@@ -42,13 +46,18 @@ struct AttnFaParams {
   // (0: issuer A, 1: softmax warp 4, 2: issuer B, 3: softmax warp 8).  nullptr = off.
   unsigned long long* trace;
   int stagger_cycles;  // initial lag of tile B's softmax group behind tile A's (see the softmax role)
+  // Trailing query rows [n_tiles*128, T) (at most 8) handled by warp 2 with mma.sync from the K/V blocks that
+  // are in shared memory anyway (0 = none: the tiles cover every row).
+  int tail_rows;
+  const __half* qkv;  // [n_seq*T, 3*H*64]
+  __half* ctx;        // [n_seq*T, H*64]
 };
 constexpr int kFaTraceCap = 2048;
 
 constexpr int kFaThreads = 384;
 constexpr int kFaKvStages = 4;
 constexpr int kFaTile = 128 * 64 * 2;  // 16 KB: 128 rows x 64 fp16
-constexpr int kFaSmemBytes = kFaTile * (4 + 2 * kFaKvStages + 1) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kFaSmemBytes = kFaTile * (4 + 2 * kFaKvStages + 1) + 1024 /*align*/ + 256 /*barriers*/ + 1024 /*tail P*/;
 constexpr int kFaOCols = 80;           // 64 head dims + 16 copies of the row sum
 constexpr float kFaRescaleThreshold = 11.0f;  // log2 units: P <= 2^11 (fp16 overflows at 2^16)
 
@@ -102,6 +111,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   uint64_t* o_full = pv_done + 2;               // [2]  per tile: last PV of the item retired
   uint64_t* o_free = o_full + 2;                // [2]  per tile: O read out (count 4)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+  __half* sTailP = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [8 queries][64 keys]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int T = p.T;
@@ -126,7 +136,8 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       mbar_init(&o_full[s], 1);
       mbar_init(&o_free[s], 4);
     }
-    for (int s = 0; s < kFaKvStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 2); }  // both issuers release
+    // K/V blocks are released by both issuers and, when there are trailing rows, by the tail warp
+    for (int s = 0; s < kFaKvStages; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], p.tail_rows > 0 ? 3 : 2); }
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -281,6 +292,140 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         if ((b || i + 1 == nsub) && issuer) umma_commit(&kv_empty[st]);
         __syncwarp();
         trace(0x18 + t);  // PV(i) [+ S(i+2)] issued
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------------------------------------------ trailing query rows (see header)
+    //   S^T[key, q] = K[key, :] . Q[q, :]        A = K rows (ldmatrix from the 128B-swizzled tile), B = Q from global
+    //   O^T[dim, q] = sum_key V[key, dim] P^T[key, q]   A = V^T (ldmatrix.trans), B = P^T via a 1 KB smem transpose
+    // C-fragment: thread (g = lane/4, t4 = lane%4) holds rows (g, g+8) x queries (2 t4, 2 t4 + 1).
+    if (p.tail_rows > 0) {
+      const int g = lane >> 2, t4 = lane & 3;
+      const int q_first = p.n_tiles * 128;
+      constexpr float kLog2e = 1.4426950408889634f;
+      uint32_t kv_cnt = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, kv_cnt += nkb) {
+        int pair, seq, head;
+        decode(item, pair, seq, head);
+        if (pair != 0) {  // the tail of this (sequence, head) belongs to its first item; still release the blocks
+          for (int j = 0; j < nkb; ++j) {
+            const uint32_t c = kv_cnt + j;
+            mbar_wait(&kv_full[c % kFaKvStages], (c / kFaKvStages) & 1);
+            if (lane == 0) mbar_arrive(&kv_empty[c % kFaKvStages]);
+            __syncwarp();
+          }
+          continue;
+        }
+        // Q as the B operand: b0 = Q[q = g][16 ks + 2 t4, +1], b1 = Q[g][16 ks + 2 t4 + 8, +9]; rows >= tail are 0
+        uint32_t qb[4][2];
+        {
+          const __half* qrow = p.qkv + (static_cast<long long>(seq) * T + q_first + g) * (3 * d) + head * 64;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            qb[ks][0] = g < p.tail_rows ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 2 * t4) : 0u;
+            qb[ks][1] = g < p.tail_rows ? *reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 2 * t4 + 8) : 0u;
+          }
+        }
+        float o[4][4];  // O^T: 4 tiles of 16 dims; c0,c2 <-> query 2 t4, c1,c3 <-> query 2 t4 + 1
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // queries 2 t4, 2 t4 + 1
+        for (int j = 0; j < nkb; ++j) {
+          const uint32_t c = kv_cnt + j;
+          const int st = c % kFaKvStages;
+          mbar_wait(&kv_full[st], (c / kFaKvStages) & 1);
+          const uint32_t sk = smem_u32(sKV + st * 2 * kFaTile), sv = sk + kFaTile;
+          const int nsb = min(2, (T - j * 128 + 63) >> 6);
+          for (int sb = 0; sb < nsb; ++sb) {
+            const int key0 = sb * 64, rem = T - j * 128 - key0;  // valid keys in this 64-key sub-block (>= 1)
+            float sc[4][4];  // S^T: 4 tiles of 16 keys
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+              sc[mt][0] = sc[mt][1] = sc[mt][2] = sc[mt][3] = 0.f;
+              const int key = key0 + mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                uint32_t a[4];
+                const uint32_t addr = sk + key * 128 + (((ks * 2 + (lane >> 4)) ^ (key & 7)) << 4);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(sc[mt][0]), "+f"(sc[mt][1]), "+f"(sc[mt][2]), "+f"(sc[mt][3])
+                             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(qb[ks][0]), "r"(qb[ks][1]));
+              }
+            }
+            // keys >= T do not exist; running maximum per query over the keys (registers, then the 8 lane groups)
+            float mx0 = m0, mx1 = m1;
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+              if (mt * 16 + g >= rem) { sc[mt][0] = -INFINITY; sc[mt][1] = -INFINITY; }
+              if (mt * 16 + g + 8 >= rem) { sc[mt][2] = -INFINITY; sc[mt][3] = -INFINITY; }
+              mx0 = fmaxf(mx0, fmaxf(sc[mt][0], sc[mt][2]));
+              mx1 = fmaxf(mx1, fmaxf(sc[mt][1], sc[mt][3]));
+            }
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) {
+              mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, off));
+              mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, off));
+            }
+            const float a0 = exp2f((m0 - mx0) * kLog2e), a1 = exp2f((m1 - mx1) * kLog2e);  // 0 on the first sub-block
+            m0 = mx0; m1 = mx1;
+            float r0 = 0.f, r1 = 0.f;
+            __syncwarp();  // the previous sub-block's P^T has been consumed by every lane
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) {
+              const float p00 = exp2f((sc[mt][0] - mx0) * kLog2e), p01 = exp2f((sc[mt][1] - mx1) * kLog2e);
+              const float p10 = exp2f((sc[mt][2] - mx0) * kLog2e), p11 = exp2f((sc[mt][3] - mx1) * kLog2e);
+              r0 += p00 + p10; r1 += p01 + p11;
+              sTailP[(2 * t4) * 64 + mt * 16 + g] = __float2half_rn(p00);
+              sTailP[(2 * t4 + 1) * 64 + mt * 16 + g] = __float2half_rn(p01);
+              sTailP[(2 * t4) * 64 + mt * 16 + g + 8] = __float2half_rn(p10);
+              sTailP[(2 * t4 + 1) * 64 + mt * 16 + g + 8] = __float2half_rn(p11);
+            }
+#pragma unroll
+            for (int off = 4; off < 32; off <<= 1) {
+              r0 += __shfl_xor_sync(0xffffffffu, r0, off);
+              r1 += __shfl_xor_sync(0xffffffffu, r1, off);
+            }
+            l0 = l0 * a0 + r0; l1 = l1 * a1 + r1;
+#pragma unroll
+            for (int dt = 0; dt < 4; ++dt) { o[dt][0] *= a0; o[dt][2] *= a0; o[dt][1] *= a1; o[dt][3] *= a1; }
+            __syncwarp();
+            // O^T += V^T P^T.  B operand from the transpose buffer: b0 = P[q = g][16 ks + 2 t4, +1], b1 = .. + 8
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&sTailP[g * 64 + ks * 16 + 2 * t4]);
+              const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&sTailP[g * 64 + ks * 16 + 2 * t4 + 8]);
+              const int key = key0 + ks * 16 + (lane & 7) + ((lane >> 4) & 1) * 8;
+#pragma unroll
+              for (int dt = 0; dt < 4; ++dt) {
+                uint32_t a[4];
+                const uint32_t addr = sv + key * 128 + (((dt * 2 + ((lane >> 3) & 1)) ^ (key & 7)) << 4);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]) : "r"(addr));
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(o[dt][0]), "+f"(o[dt][1]), "+f"(o[dt][2]), "+f"(o[dt][3])
+                             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+              }
+            }
+          }
+          __syncwarp();  // every lane has finished reading this K/V block
+          if (lane == 0) mbar_arrive(&kv_empty[st]);
+        }
+        // ctx[q][dim] = O^T[dim][q] / l[q]
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+        __half* out = p.ctx + (static_cast<long long>(seq) * T + q_first) * d + head * 64;
+#pragma unroll
+        for (int dt = 0; dt < 4; ++dt) {
+          if (2 * t4 < p.tail_rows) {
+            out[static_cast<long long>(2 * t4) * d + dt * 16 + g] = __float2half_rn(o[dt][0] * i0);
+            out[static_cast<long long>(2 * t4) * d + dt * 16 + g + 8] = __float2half_rn(o[dt][2] * i0);
+          }
+          if (2 * t4 + 1 < p.tail_rows) {
+            out[static_cast<long long>(2 * t4 + 1) * d + dt * 16 + g] = __float2half_rn(o[dt][1] * i1);
+            out[static_cast<long long>(2 * t4 + 1) * d + dt * 16 + g + 8] = __float2half_rn(o[dt][3] * i1);
+          }
+        }
       }
     }
   } else if (warp >= 4) {

@@ -563,13 +563,17 @@ static int launch_attention_fa(const CUtensorMap& qkv3, const CUtensorMap& ctx3,
     CK(cudaFuncSetAttribute(attention_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
     configured = true;
   }
+  // Trailing rows (T = 128 k + r): r <= 8 -> the kernel's tail warp; r <= 16 -> the mma.sync kernel (second launch);
+  // otherwise a normal partly filled tile.  PGIBBS_ATTN_TAIL=0 forces the partly filled tile.
   const int tail = T % 128;
-  const bool split_tail = g_attn_tail && T > 128 && tail > 0 && tail <= 16;
-  AttnFaParams p{T, H, n_seq, split_tail ? T / 128 : (T + 127) / 128, g_fa_trace, g_attn_stagger};
+  const bool any_tail = g_attn_tail && T > 128 && tail > 0 && tail <= 16;
+  const bool in_kernel = any_tail && tail <= 8 && g_attn_tail != 2;
+  AttnFaParams p{T, H, n_seq, any_tail ? T / 128 : (T + 127) / 128, g_fa_trace, g_attn_stagger,
+                 in_kernel ? tail : 0, qkv, ctx};
   const int n_items = n_seq * H * ((p.n_tiles + 1) / 2);
   attention_fa_kernel<<<std::min(g_num_sms, n_items), kFaThreads, kFaSmemBytes, st>>>(qkv3, ctx3, p);
   CK(cudaGetLastError());
-  if (split_tail) {
+  if (any_tail && !in_kernel) {
     const int d = H * 64;
     AttnParams tp{qkv, ctx, T, 3 * d, d, d, 2 * d, 1, 0, 1, T, T - tail};
     TRY(launch_attention(tp, n_seq, H, 64, st));
