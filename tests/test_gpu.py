@@ -141,7 +141,7 @@ def test_forward_logits_vs_oracle(arch, layers, d, H, F, shape):
     assert rms < 0.5 * LOGIT_TOL
     if (arch, layers, d) == ("esm2", 33, 1280):
         # Single-pass fp16 operands bound the worst element of the deepest rotary model at 0.9-1.2e-3 of the
-        # largest logit whatever the input (CPU emulation of the operand rounding: tools/precision_study2.py,
+        # largest logit whatever the input (CPU emulation of the operand rounding: tests/tools/precision_study2.py,
         # DESIGN.md section 3); the rms error is 3e-4.  Every other geometry sits below 1e-3 with margin.
         assert rel(got, want) < 1.5 * LOGIT_TOL
     else:

@@ -1,13 +1,13 @@
 """Stage-by-stage GPU bring-up check.  Each stage runs in its own subprocess (a device trap poisons the CUDA
 context) with a timeout, so one bad kernel cannot hide the others.  Usage (on a GPU box):
-    python tools/gpu_check.py [stage ...]      # writes gpurun_out/gpu_check.log
+    python tests/tools/gpu_check.py [stage ...]      # writes gpurun_out/gpu_check.log
 """
 import os
 import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 

@@ -1,18 +1,18 @@
 """CPU emulation of the engine's operand rounding: which rounded tensor class contributes how much of the logit
 error against the fp32 oracle (full-depth models, synthetic weights).  Not part of the product; run by hand:
-    python tools/precision_study.py [esm2|roberta_large] [fmt: f16|bf16]
+    python tests/tools/precision_study.py [esm2|roberta_large] [fmt: f16|bf16]
 """
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 
 from oracle.fair_esm import OracleModel
 from protein_gibbs_sampler_b200.config import tiny_config
 from protein_gibbs_sampler_b200.weights import synthetic_state_dict
 
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def tokens(shape, seed):

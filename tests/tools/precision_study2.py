@@ -1,12 +1,12 @@
 """Finer CPU emulation: contribution of each GEMM class (qkv / out / fc1 / fc2 / head) and operand (W / activation)
 to the logit error vs the fp32 oracle, by rounding everything EXCEPT that class-operand (leave-one-out)."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 from oracle.fair_esm import OracleModel
 from protein_gibbs_sampler_b200.config import tiny_config
 from protein_gibbs_sampler_b200.weights import synthetic_state_dict
-from tools.precision_study import tokens
+from precision_study import tokens
 
 arch = sys.argv[1] if len(sys.argv) > 1 else "esm2"
 cfg = tiny_config(arch, 33, 1280, 20, 5120)
