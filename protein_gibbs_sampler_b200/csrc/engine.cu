@@ -19,6 +19,7 @@
 #include "attention_fa.cuh"
 #include "gemm.cuh"
 #include "msa_attention.cuh"
+#include "msa_row_tc.cuh"
 #include "rowwise.cuh"
 
 namespace pg {
@@ -97,12 +98,13 @@ static int make_tmap_out(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_
 
 // Fused qkv activation viewed as [n_seq][T][3d] fp16 for the tcgen05 attention kernel: box = 64 columns (one head of
 // q, k or v) x 128 tokens of one sequence, 128B swizzle; tokens t >= T are zero-filled (never the next sequence).
-static int make_tmap_qkv3(CUtensorMap* m, const void* ptr, uint64_t n_seq, uint64_t T, uint64_t ld) {
+static int make_tmap_qkv3(CUtensorMap* m, const void* ptr, uint64_t n_seq, uint64_t T, uint64_t ld,
+                          uint32_t box_rows = 128) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[3] = {ld, T, n_seq};
   cuuint64_t strides[2] = {ld * sizeof(__half), T * ld * sizeof(__half)};
-  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t box[3] = {64, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -278,7 +280,7 @@ struct pgibbs_engine {
   float* x = nullptr;
   __half *h = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr, *hs = nullptr;
   float *g = nullptr, *logits = nullptr, *scores = nullptr;
-  CUtensorMap m_h, m_ctx, m_ffn, m_hs, m_qkv3, m_ctx3;
+  CUtensorMap m_h, m_ctx, m_ffn, m_hs, m_qkv3, m_ctx3, m_qkv3_keys;  // _keys: box of all (<= 256) key rows
   GemmPlan g_qkv, g_o, g_fc1, g_fc2, g_dense;
   // schedule / rng
   int32_t* positions = nullptr;
@@ -459,6 +461,7 @@ static int ensure_shape(pgibbs_engine* e, int B, int R, int T) {
   TRY(make_tmap_2d(&e->m_hs, e->hs, M, d, d, kBM));
   TRY(make_tmap_qkv3(&e->m_qkv3, e->qkv, static_cast<uint64_t>(B) * R, T, 3 * d));
   TRY(make_tmap_qkv3(&e->m_ctx3, e->ctx, static_cast<uint64_t>(B) * R, T, d));
+  if (T <= 256) TRY(make_tmap_qkv3(&e->m_qkv3_keys, e->qkv, static_cast<uint64_t>(B) * R, T, 3 * d, (T + 15) & ~15));
   const int hd = d / e->cfg.heads;
   e->g_qkv = pick_gemm_plan(e->M, 3 * d, hd >= 64 ? 64 : 32);
   e->g_o = pick_gemm_plan(e->M, d, 16);
@@ -581,6 +584,33 @@ static int launch_attention_fa(const CUtensorMap& qkv3, const CUtensorMap& ctx3,
   return 0;
 }
 
+// Tied row attention of the MSA Transformer: tcgen05 kernel for head_dim 64 and alignments of up to 256 columns
+// (msa_row_tc.cuh), the mma.sync kernels otherwise (PGIBBS_MSA_ROW=legacy forces them).
+static int run_msa_row_attention(pgibbs_engine* e) {
+  const auto& c = e->cfg;
+  const int hd = c.embed_dim / c.heads;
+  static int legacy = -1;
+  if (legacy < 0) { const char* v = getenv("PGIBBS_MSA_ROW"); legacy = (v && !strcmp(v, "legacy")) ? 1 : 0; }
+  ProfScope ps(e, "msa_row_attention");
+  if (hd == 64 && e->T <= 256 && !legacy) {
+    MsaRowParams p{e->R, e->T, c.heads, (e->T + 15) & ~15, 0};
+    p.stages = std::min(8, (227 * 1024 - 2 * kMrQBytes - 2048) / mr_stage_bytes(p.NK));
+    const int smem = mr_smem_bytes(p.NK, p.stages);
+    static int configured = 0;
+    if (smem > configured) {
+      CK(cudaFuncSetAttribute(msa_row_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured = smem;
+    }
+    dim3 grid((e->T + 127) / 128, c.heads, e->B);
+    msa_row_attention_tc_kernel<<<grid, kMrThreads, smem, e->stream>>>(e->m_qkv3, e->m_qkv3_keys, e->m_ctx3, p);
+    CK(cudaGetLastError());
+    return 0;
+  }
+  if (const char* m = launch_msa_row_attention(e->qkv, e->ctx, e->scores, e->B, e->R, e->T, c.heads, hd, e->stream))
+    return fail("%s", m);
+  return 0;
+}
+
 static int run_attention(pgibbs_engine* e) {
   const int d = e->cfg.embed_dim, H = e->cfg.heads, hd = d / H;
   ProfScope ps(e, "attention");
@@ -630,10 +660,7 @@ static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int it
       GemmParams q = gp(M, 3 * d, d, l.bqkv, e->qkv, 3 * d);
       q.q_cols = d; q.q_scale = row_scale; q.rope_cols = 0; q.head_dim = hd; q.seq_len = e->T;
       TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->g_qkv, e->m_h, l.m_wqkv, q));
-      {
-        ProfScope ps(e, "msa_row_attention");
-        if (const char* m = launch_msa_row_attention(e->qkv, e->ctx, e->scores, e->B, e->R, e->T, c.heads, hd, st)) return fail("%s", m);
-      }
+      TRY(run_msa_row_attention(e));
       TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->g_o, e->m_ctx, l.m_wo, gp(M, d, d, l.bo, e->x, d)));
       // column attention
       TRY(run_ln(e, e->x, l.lncw, l.lncb, e->h, M, nullptr, 0));
