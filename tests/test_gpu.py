@@ -124,6 +124,10 @@ def _tokens(cfg, shape, seed):
     ("esm2", 33, 1280, 20, 5120, (2, 40)),                  # full-depth ESM-2 650M (config 4 model)
     ("msa_transformer", 2, 128, 2, 256, (2, 4, 17)), ("msa_transformer", 2, 768, 12, 3072, (1, 8, 33)),
     ("msa_transformer", 2, 128, 2, 256, (2, 1, 9)),         # single-row MSA (pgen_msa_revised --alignment_size 1)
+    ("msa_transformer", 2, 128, 2, 256, (1, 3, 200)),       # tcgen05 tied row attention, two query tiles
+    ("msa_transformer", 2, 128, 2, 256, (1, 5, 129)),       # ... second tile with a single valid row (L = 128)
+    ("msa_transformer", 2, 128, 2, 256, (1, 2, 300)),       # wider than 256 columns: mma.sync row attention
+    ("msa_transformer", 2, 128, 4, 256, (1, 3, 70)),        # head_dim 32: mma.sync kernels throughout
     ("msa_transformer", 12, 768, 12, 3072, (1, 6, 40)),     # full-depth MSA-1b (config 3 model)
 ])
 def test_forward_logits_vs_oracle(arch, layers, d, H, F, shape):
