@@ -197,17 +197,28 @@ class ESM_MSA_sampler():
         return next(self.log_likelihood_batch([msa], target_index, with_masking, verbose, count_gaps, mask_distance))
 
     def log_likelihood_batch(self, msa_list, target_index=0, with_masking=True, verbose=False, count_gaps=False,
-                             mask_distance=float("inf"), batch_size=None) -> Iterator[Tuple[float, List[float]]]:
-        """Pseudo-log-likelihood of row ``target_index`` of each MSA (reference :319-432)."""
+                             mask_distance=float("inf"), batch_size=1) -> Iterator[Tuple[float, List[float]]]:
+        """Pseudo-log-likelihood of row ``target_index`` of each MSA (reference esm_msa_sampler.py:319-432): strided
+        masking (copy i of the MSA masks positions i, i+n, ... of the target row, n = min(mask_distance, L)), gap
+        positions of the target skipped unless ``count_gaps``, values listed copy by copy as the reference does, mean
+        accumulated in float32 like its 0-d tensor sum.  Each MSA is scored on its own, so every forward is over
+        equal-length rows and no <pad> reaches the engine."""
         alphabet = self.model.alphabet
+        gap_tokens = {alphabet.get_idx(c) for c in ESM_MSA_GAP_CHARACTERS}
+        start = 1 if alphabet.prepend_bos else 0
         for msa in msa_list:
             cleaned = [self.clean_seed_seq(s) for s in msa]
-            toks = self.model.batch_converter([(str(i), s) for i, s in enumerate(cleaned)])[2]  # [1,R,C]
-            target = cleaned[target_index]
-            L = len(target)
-            scored = [p for p in range(L) if count_gaps or target[p] not in ESM_MSA_GAP_CHARACTERS]
-            true_toks = toks[0, target_index]
-            vals = {}
+            toks = self.model.batch_converter([[(str(i), s) for i, s in enumerate(cleaned)]])[2]  # [1, R, C]
+            L = len(cleaned[target_index])
+            true_toks = toks[0, target_index].tolist()
+            values = []
+
+            def collect(lp_row, positions):
+                for pos in positions:
+                    tok = true_toks[start + pos]
+                    if count_gaps or tok not in gap_tokens:
+                        values.append(lp_row[start + pos, tok].item())
+
             if with_masking:
                 n_copies = int(min(mask_distance, L))
                 bs = batch_size or n_copies
@@ -215,14 +226,16 @@ class ESM_MSA_sampler():
                     chunk = range(b0, min(b0 + bs, n_copies))
                     t = toks.repeat(len(chunk), 1, 1)
                     for j, i in enumerate(chunk):
-                        t[j, target_index, 1 + i:1 + L:n_copies] = alphabet.mask_idx
+                        t[j, target_index, start + i:start + L:n_copies] = alphabet.mask_idx
+                    if verbose:
+                        print(t[:, target_index])
                     lp = torch.log_softmax(self.model.model(t)["logits"], dim=-1)
                     for j, i in enumerate(chunk):
-                        for pos in range(i, L, n_copies):
-                            vals[pos] = lp[j, target_index, 1 + pos, true_toks[1 + pos]].item()
+                        collect(lp[j, target_index], range(i, L, n_copies))
             else:
                 lp = torch.log_softmax(self.model.model(toks)["logits"], dim=-1)
-                for pos in range(L):
-                    vals[pos] = lp[0, target_index, 1 + pos, true_toks[1 + pos]].item()
-            ordered = [vals[p] for p in scored]
-            yield (float(sum(ordered) / max(len(ordered), 1)), ordered)
+                collect(lp[0, target_index], range(L))
+            total = np.float32(0.0)
+            for v in values:
+                total = np.float32(total + np.float32(v))
+            yield (float(total / np.float32(len(values))) if values else float("nan"), values)

@@ -271,4 +271,7 @@ class ESM_sampler():
             else:
                 lp = torch.log_softmax(self.model.model(true_toks[None])["logits"], dim=-1)[0]
                 ordered = [lp[start + pos, true_toks[start + pos]].item() for pos in range(L)]
-            yield (float(sum(ordered) / L), ordered)
+            total = np.float32(0.0)   # the reference sums 0-d float32 tensors
+            for v in ordered:
+                total = np.float32(total + np.float32(v))
+            yield (float(total / np.float32(L)), ordered)
