@@ -102,10 +102,13 @@ def pgen_msa(templates_path, references_path, output_path, seqs_per_template, ke
                     exclude_positions = apply_gap_threshold(alignment, gap_percent_threshold)
                 else:            # original behaviour: the template is the LAST row
                     alignment[0], alignment[-1] = alignment[-1], alignment[0]
-                for i in range(seqs_per_template):
-                    new_seq = gibbs_sampler.generate_single(alignment, steps=steps, passes=passes, burn_in=burn_in,
-                                                            k=top_k, target_index=-1 if legacy else 0,
-                                                            exclude_positions=exclude_positions)
+                # all seqs_per_template chains of this template as one device batch (the reference runs them one by
+                # one, a batch-1 forward per step: pgen_msa_revised.py:107-115); same RNG consumption order
+                new_seqs = gibbs_sampler.generate_single_batch(alignment, seqs_per_template, steps=steps, passes=passes,
+                                                               burn_in=burn_in, k=top_k,
+                                                               target_index=-1 if legacy else 0,
+                                                               exclude_positions=exclude_positions)
+                for i, new_seq in enumerate(new_seqs):
                     print(f">{i}_{template_name}\n{new_seq.replace('-', '')}", file=outfile, flush=True)
                     pbar.update(1)
     finally:

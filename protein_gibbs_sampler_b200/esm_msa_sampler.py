@@ -191,6 +191,63 @@ class ESM_MSA_sampler():
                 i = j
         return self.untokenize_batch(engine.get_tokens())[target_index]
 
+    def generate_single_batch(self, seed_msa, n, steps=10, passes=3, burn_in=1, target_index=0, k=1,
+                              exclude_positions=None):
+        """``n`` independent ``generate_single`` chains on ONE device batch (the reference's
+        `pgen_msa_revised.py:107-115` calls generate_single `seqs_per_template` times, each a batch-1 forward per step).
+
+        Equivalent to ``[self.generate_single(...) for _ in range(n)]``: the position shuffles (Python ``random``) and,
+        in replay mode, the Exp(1) variates (torch) are drawn call by call in that order before anything runs -- neither
+        stream depends on the model -- and chain c then follows call c's schedule.  Bin sizes depend only on the number
+        of positions, so all chains share every step's P."""
+        engine = self.model.model.require_engine()
+        excluded = {i + 1 for i in (exclude_positions or [])}
+        sequence_length = len(seed_msa[0])
+        R = len(seed_msa)
+        # ---- pre-draw, call-major: schedule[c][pass] = list of bins; noise[c][pass][group] (replay mode)
+        schedules, noises = [], []
+        for _ in range(n):
+            positions = [x for x in range(1, sequence_length + 1) if x not in excluded]
+            per_pass, per_pass_noise = [], []
+            for pass_num in range(passes):
+                random.shuffle(positions)
+                bins = partition(positions, steps)
+                per_pass.append([list(b) for b in bins])
+                if self.rng == "replay":
+                    burnin = float("inf") if pass_num < burn_in else 0
+                    group_noise, i = [], 0
+                    while i < len(bins):
+                        j = i
+                        while j < len(bins) and len(bins[j]) == len(bins[i]):
+                            j += 1
+                        group_noise.append(draw_replay_noise(j - i, len(bins[i]), len(self.valid_aa_idx), k, burnin))
+                        i = j
+                    per_pass_noise.append(group_noise)
+            schedules.append(per_pass)
+            noises.append(per_pass_noise)
+        engine.set_tokens(self.get_init_msa(seed_msa, sequence_length, n))
+        for pass_num in range(passes):
+            bins0 = schedules[0][pass_num]
+            burnin = float("inf") if pass_num < burn_in else 0
+            i, g = 0, 0
+            while i < len(bins0):
+                j = i
+                while j < len(bins0) and len(bins0[j]) == len(bins0[i]):
+                    j += 1
+                P = len(bins0[i])
+                pos = np.asarray([[schedules[c][pass_num][st] for c in range(n)] for st in range(i, j)], dtype=np.int32)
+                engine.set_schedule(pos, j - i, P, n * P, P, False)
+                if self.rng == "replay":
+                    stride = noises[0][pass_num][g][1]
+                    engine.set_noise(torch.cat([noises[c][pass_num][g][0] for c in range(n)], dim=1), stride)
+                else:
+                    engine.set_noise(None)
+                    engine.set_device_rng(int(torch.randint(0, 2 ** 62, (1,)).item()))
+                engine.run_single(0, j - i, burnin, k, None, -1, target_index, self.valid_aa_idx)
+                i, g = j, g + 1
+        rows = self.untokenize_batch(engine.get_tokens())
+        return [rows[c * R + (target_index % R)] for c in range(n)]
+
     # ------------------------------------------------------------------ scoring (shares the forward)
     def log_likelihood(self, msa, target_index=0, with_masking=True, verbose=False, count_gaps=False,
                        mask_distance=float("inf")) -> Tuple[float, List[float]]:

@@ -256,3 +256,23 @@ def test_full_size_properties_config2():
     assert torch.equal(sub, a[:16])                                      # chains are independent Markov chains
     logits = eng.forward_logits(toks[:2])
     assert logits.shape == (2, 258, 33) and bool(torch.isfinite(logits).all())
+
+
+def test_generate_single_batch_equals_sequential_calls():
+    """n generate_single chains as one device batch give what n sequential calls give (replay mode:
+    shuffles and Exp(1) variates are pre-drawn in the sequential calls' order)."""
+    from protein_gibbs_sampler_b200.config import tiny_config
+    cfg = tiny_config("msa_transformer", 2, 128, 2, 256)
+    s, _ = make(cfg, 3)
+    msa = ["MKTAYIAK-RQ", "MKSAY-AKQRQ", "MRTAYIAKQ-Q", "M-TAYLAKQRQ"]
+    for kw in (dict(steps=3, passes=2, burn_in=1, target_index=0, k=1),
+               dict(steps=2, passes=3, burn_in=1, target_index=-1, k=2, exclude_positions=[0, 4]),
+               dict(steps=11, passes=1, burn_in=0, target_index=2, k=3)):
+        random.seed(5)
+        torch.manual_seed(5)
+        want = [s.generate_single(msa, **kw) for _ in range(3)]
+        random.seed(5)
+        torch.manual_seed(5)
+        got = s.generate_single_batch(msa, 3, **kw)
+        assert got == want, (kw, got, want)
+        assert len(set(want)) > 1 or kw["k"] == 1   # the chains really are different draws
