@@ -18,7 +18,9 @@ extern "C" {
 
 typedef struct pgibbs_engine pgibbs_engine;
 
-enum { PGIBBS_ARCH_ESM1B = 0, PGIBBS_ARCH_ESM2 = 1, PGIBBS_ARCH_MSA = 2 };
+/* ESM1B: ESM-1b / ESM-1v (learned positions); ESM2: rotary; MSA: MSA Transformer; ESM1: esm1_t6/t12/t34 (sinusoidal
+ * positions supplied as the `embed_positions.weight` table, sqrt(d) embedding scale, bias key/value, untied output). */
+enum { PGIBBS_ARCH_ESM1B = 0, PGIBBS_ARCH_ESM2 = 1, PGIBBS_ARCH_MSA = 2, PGIBBS_ARCH_ESM1 = 3 };
 
 /* Geometry of the model behind `model.model(batch)["logits"]` (esm_sampler.py:223, esm_msa_sampler.py:236). */
 typedef struct {

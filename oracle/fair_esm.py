@@ -276,6 +276,80 @@ class ESMOracle(torch.nn.Module):
 
 
 # --------------------------------------------------------------------------
+# ESM-1 (esm1_t6 / t12 / t34; ProteinBertModel with arch != roberta_large, esm/model/esm1.py)
+# --------------------------------------------------------------------------
+
+def sinusoidal_positions(tokens, dim, padding_idx):
+    """esm/modules.py SinusoidalPositionalEmbedding: table row = position + padding_idx + 1 for non-pad tokens."""
+    B, T = tokens.shape
+    n = padding_idx + 1 + T
+    half = dim // 2
+    step = math.log(10000) / (half - 1)
+    freq = torch.exp(torch.arange(half, dtype=torch.float) * -step)
+    ang = torch.arange(n, dtype=torch.float).unsqueeze(1) * freq.unsqueeze(0)
+    tbl = torch.cat([torch.sin(ang), torch.cos(ang)], dim=1).view(n, -1)
+    if dim % 2 == 1:
+        tbl = torch.cat([tbl, torch.zeros(n, 1)], dim=1)
+    tbl[padding_idx, :] = 0
+    mask = tokens.ne(padding_idx)
+    pos = (torch.arange(T) + padding_idx + 1).expand_as(tokens) * mask.long() + padding_idx * (1 - mask.long())
+    return tbl.index_select(0, pos.reshape(-1)).view(B, T, -1)
+
+
+class ESM1Oracle(torch.nn.Module):
+    """embed_scale sqrt(d), sinusoidal positions, no embedding LayerNorms / token dropout, pre-LN layers whose
+    attention has one learned bias key/value appended after the sequence (add_bias_kv), LayerNorm eps 1e-12
+    (ESM1LayerNorm), logits = F.linear(x, embed_out, embed_out_bias)."""
+
+    def __init__(self, cfg: dict, state_dict: Dict[str, torch.Tensor], hook=None):
+        super().__init__()
+        self.cfg = dict(cfg)
+        self.sd = {k: v.detach().float().clone() for k, v in state_dict.items()}
+        self.hook = hook
+        self.alphabet = Alphabet.from_architecture("ESM-1")
+        self.mm = torch.matmul
+
+    def to(self, *a, **k):
+        return self
+
+    def _lin(self, x, prefix):
+        return self.mm(x, self.sd[prefix + ".weight"].t()) + self.sd[prefix + ".bias"]
+
+    def forward(self, tokens, repr_layers=(), **kw):
+        cfg, sd, a = self.cfg, self.sd, self.alphabet
+        d, H, eps = cfg["embed_dim"], cfg["heads"], 1e-12
+        Dh = d // H
+        B, T = tokens.shape
+        pad = tokens.eq(a.padding_idx)
+        x = math.sqrt(d) * F.embedding(tokens, sd["embed_tokens.weight"])
+        x = x + sinusoidal_positions(tokens, d, a.padding_idx)
+        x = x * (1 - pad.unsqueeze(-1).type_as(x))
+        if self.hook is not None:
+            self.hook("embed", x)
+        for i in range(cfg["layers"]):
+            p = "layers.%d." % i
+            h = layer_norm(x, sd[p + "self_attn_layer_norm.weight"], sd[p + "self_attn_layer_norm.bias"], eps)
+            q = self._lin(h, p + "self_attn.q_proj") * (Dh ** -0.5)
+            k = torch.cat([self._lin(h, p + "self_attn.k_proj"), sd[p + "self_attn.bias_k"].view(1, 1, d).expand(B, 1, d)], 1)
+            v = torch.cat([self._lin(h, p + "self_attn.v_proj"), sd[p + "self_attn.bias_v"].view(1, 1, d).expand(B, 1, d)], 1)
+            q = q.view(B, T, H, Dh).transpose(1, 2)
+            k = k.view(B, T + 1, H, Dh).transpose(1, 2)
+            v = v.view(B, T + 1, H, Dh).transpose(1, 2)
+            s = self.mm(q, k.transpose(-1, -2))
+            if pad.any():
+                s = s.masked_fill(torch.cat([pad, pad.new_zeros(B, 1)], 1)[:, None, None, :], float("-inf"))
+            pr = torch.softmax(s, dim=-1, dtype=torch.float32)
+            ctx = self.mm(pr, v).transpose(1, 2).reshape(B, T, d)
+            x = x + self._lin(ctx, p + "self_attn.out_proj")
+            h = layer_norm(x, sd[p + "final_layer_norm.weight"], sd[p + "final_layer_norm.bias"], eps)
+            x = x + self._lin(gelu_erf(self._lin(h, p + "fc1")), p + "fc2")
+            if self.hook is not None:
+                self.hook("layer%d" % i, x)
+        bias = sd.get("embed_out_bias")
+        return {"logits": F.linear(x, sd["embed_out"], bias), "representations": {}}
+
+
+# --------------------------------------------------------------------------
 # MSA Transformer (esm/model/msa_transformer.py, esm/axial_attention.py)
 # --------------------------------------------------------------------------
 
@@ -362,6 +436,8 @@ class OracleModel:
     def __init__(self, cfg, state_dict, hook=None):
         if cfg["arch"] == "msa_transformer":
             self.model = MSAOracle(cfg, state_dict, hook)
+        elif cfg["arch"] == "esm1":
+            self.model = ESM1Oracle(cfg, state_dict, hook)
         else:
             self.model = ESMOracle(cfg, state_dict, hook)
         self.alphabet = self.model.alphabet

@@ -39,6 +39,12 @@ class Alphabet:
         return cls(("<cls>", "<pad>", "<eos>", "<unk>"), ("<mask>",), True, True)
 
     @classmethod
+    def esm1(cls):
+        """ESM-1 (esm1_t6/t12/t34) alphabet: 35 tokens, <null_0>=0 ... <cls>=32, <mask>=33, <sep>=34; bos only
+        (pinned by the reference's fixtures, test_esm_sampler.py:43-66)."""
+        return cls(("<null_0>", "<pad>", "<eos>", "<unk>"), ("<cls>", "<mask>", "<sep>"), True, False)
+
+    @classmethod
     def msa(cls):
         """MSA Transformer alphabet: same ids, no <eos> appended."""
         return cls(("<cls>", "<pad>", "<eos>", "<unk>"), ("<mask>",), True, False, use_msa=True)

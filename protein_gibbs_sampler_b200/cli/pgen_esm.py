@@ -10,9 +10,9 @@ from ..esm_sampler import ESM_sampler
 from ..fasta import RawAndDefaultsFormatter, write_sequential_fasta
 from . import add_weight_flags, build_model, spec_args
 
-# reference names (pgen_esm.py:10) that this engine implements, plus the ESM-2 family (BASELINE configs 1 and 4);
-# esm6 / esm12 / esm34 are the ESM-1 (sinusoidal) family: SURVEY section 8(f) item 2, not built yet.
-model_map = {"esm1b": models.ESM1b, "esm1v": models.ESM1v, "esm2_t6_8M": models.ESM2_t6_8M,
+# the reference's names (pgen_esm.py:10) plus the ESM-2 family (BASELINE configs 1 and 4)
+model_map = {"esm1b": models.ESM1b, "esm6": models.ESM6, "esm12": models.ESM12, "esm34": models.ESM34,
+             "esm1v": models.ESM1v, "esm2_t6_8M": models.ESM2_t6_8M,
              "esm2_t30_150M": models.ESM2_t30_150M, "esm2_t33_650M": models.ESM2_t33_650M}
 
 EPILOG = """

@@ -248,6 +248,7 @@ struct LayerW {
   __half *wqkv = nullptr, *wo = nullptr, *w1 = nullptr, *w2 = nullptr;
   float *bqkv = nullptr, *bo = nullptr, *b1 = nullptr, *b2 = nullptr;
   const float *ln1w = nullptr, *ln1b = nullptr, *ln2w = nullptr, *ln2b = nullptr;
+  const float *bias_k = nullptr, *bias_v = nullptr;  // ESM-1 add_bias_kv
   // MSA column attention
   __half *c_wqkv = nullptr, *c_wo = nullptr;
   float *c_bqkv = nullptr, *c_bo = nullptr;
@@ -275,7 +276,10 @@ struct pgibbs_engine {
   float2* rope = nullptr;
   int rope_T = 0;
   // activations
-  int B = 0, R = 0, T = 0, n_seq = 0, M = 0;
+  // T = token rows per sequence on the device = Tu (the caller's tokens per sequence) + 1 for ESM-1, whose extra
+  // last row is the bias key/value slot of fair-esm's add_bias_kv (its q / residual are computed and ignored)
+  int B = 0, R = 0, T = 0, Tu = 0, n_seq = 0, M = 0;
+  float ln_eps = 1e-5f, embed_scale = 1.0f;
   int32_t* tokens = nullptr;
   float* x = nullptr;
   __half *h = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr, *hs = nullptr;
@@ -423,7 +427,7 @@ static int build_weight_maps(pgibbs_engine* e) {
       TRY(make_tmap_2d(&l.m_cwo, l.c_wo, d, d, d, e->g_o.b_box()));
     }
   }
-  TRY(make_tmap_2d(&e->m_wdense, e->w_dense, d, d, d, e->g_dense.b_box()));
+  if (e->w_dense) TRY(make_tmap_2d(&e->m_wdense, e->w_dense, d, d, d, e->g_dense.b_box()));
   return 0;
 }
 
@@ -433,10 +437,12 @@ static int ensure_shape(pgibbs_engine* e, int B, int R, int T) {
   if (e->cfg.arch != PGIBBS_ARCH_ESM2 && T > e->cfg.max_positions)
     return fail("sequence of %d tokens exceeds the learned position table (%d)", T, e->cfg.max_positions);
   if (e->cfg.arch == PGIBBS_ARCH_MSA && R > 1024) return fail("MSA depth %d exceeds 1024", R);
-  if (B == e->B && R == e->R && T == e->T) return 0;
+  if (B == e->B && R == e->R && T == e->Tu) return 0;
   CK(cudaStreamSynchronize(e->stream));
   free_activations(e);
   const int d = e->cfg.embed_dim, F = e->cfg.ffn_dim, V = e->cfg.vocab;
+  e->Tu = T;
+  if (e->cfg.arch == PGIBBS_ARCH_ESM1) T += 1;  // the bias key/value slot
   e->B = B; e->R = R; e->T = T; e->n_seq = B * R;
   const size_t M = static_cast<size_t>(B) * R * T;
   e->M = static_cast<int>(M);
@@ -483,7 +489,7 @@ static int ensure_shape(pgibbs_engine* e, int B, int R, int T) {
 static int run_ln(pgibbs_engine* e, const float* x, const float* w, const float* b, __half* out, int rows,
                   const Schedule* gather, int iter) {
   LnParams p{};
-  p.x = x; p.w = w; p.b = b; p.out = out; p.rows_out = rows; p.d = e->cfg.embed_dim; p.eps = 1e-5f;
+  p.x = x; p.w = w; p.b = b; p.out = out; p.rows_out = rows; p.d = e->cfg.embed_dim; p.eps = e->ln_eps;
   if (gather) p.sched = *gather; else p.sched.positions = nullptr;
   p.iter = iter; p.T = e->T;
   ProfScope ps(e, "layernorm");
@@ -493,6 +499,17 @@ static int run_ln(pgibbs_engine* e, const float* x, const float* w, const float*
   else if (vpl <= 6) layernorm_kernel<true, 6><<<grid, 256, 0, e->stream>>>(p);
   else if (vpl <= 10) layernorm_kernel<true, 10><<<grid, 256, 0, e->stream>>>(p);
   else layernorm_kernel<true, kMaxVecPerLane><<<grid, 256, 0, e->stream>>>(p);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// g[i] = x[row of scheduled position i] (fp32 copy, no LayerNorm): the LM-head input of ESM-1.
+static int run_gather_f32(pgibbs_engine* e, const float* x, float* out, int rows, const Schedule& gather, int iter) {
+  LnParams p{};
+  p.x = x; p.w = nullptr; p.b = nullptr; p.out = out; p.rows_out = rows; p.d = e->cfg.embed_dim; p.eps = e->ln_eps;
+  p.sched = gather; p.iter = iter; p.T = e->T; p.identity = 1;
+  ProfScope ps(e, "layernorm");
+  layernorm_kernel<false, kMaxVecPerLane><<<(rows + 7) / 8, 256, 0, e->stream>>>(p);
   CK(cudaGetLastError());
   return 0;
 }
@@ -640,12 +657,13 @@ static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int it
     p.tok_emb = raw_get(e, "embed_tokens.weight", -1);
     p.pos_emb = c.arch == PGIBBS_ARCH_ESM2 ? nullptr : raw_get(e, "embed_positions.weight", -1);
     p.row_emb = c.arch == PGIBBS_ARCH_MSA ? raw_get(e, "msa_position_embedding", -1) : nullptr;
-    if (c.arch != PGIBBS_ARCH_ESM2) {
+    p.scale = e->embed_scale;
+    if (c.arch != PGIBBS_ARCH_ESM2 && c.arch != PGIBBS_ARCH_ESM1) {
       p.ln_w = raw_get(e, "emb_layer_norm_before.weight", -1);
       p.ln_b = raw_get(e, "emb_layer_norm_before.bias", -1);
     }
     p.x = e->x; p.n_seq = e->n_seq; p.T = e->T; p.d = d; p.rows_per_msa = e->R;
-    p.mask_idx = c.mask_idx; p.token_dropout = c.token_dropout; p.eps = 1e-5f;
+    p.mask_idx = c.mask_idx; p.token_dropout = c.token_dropout; p.eps = e->ln_eps;
     ProfScope ps(e, "embed");
     embed_kernel<<<(M + 7) / 8, 256, 0, st>>>(p);
     CK(cudaGetLastError());
@@ -682,6 +700,11 @@ static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int it
       q.rope_cols = c.arch == PGIBBS_ARCH_ESM2 ? 2 * d : 0;
       q.head_dim = hd; q.seq_len = e->T; q.rope = e->rope;
       TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->g_qkv, e->m_h, l.m_wqkv, q));
+      if (c.arch == PGIBBS_ARCH_ESM1) {  // the extra row of every sequence becomes the learned bias key / value
+        ProfScope ps(e, "bias_kv");
+        bias_kv_kernel<<<(e->n_seq * d + 255) / 256, 256, 0, st>>>(e->qkv, l.bias_k, l.bias_v, e->n_seq, e->T, d);
+        CK(cudaGetLastError());
+      }
       TRY(run_attention(e));
       TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->g_o, e->m_ctx, l.m_wo, gp(M, d, d, l.bo, e->x, d)));
     }
@@ -691,19 +714,25 @@ static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int it
   }
   // LM head on the scheduled rows only
   const int rows = n_chains * sched.P;
-  TRY(run_ln(e, e->x, raw_get(e, "emb_layer_norm_after.weight", -1), raw_get(e, "emb_layer_norm_after.bias", -1),
-             e->hs, rows, &sched, iter));
-  TRY(run_gemm(e, "gemm_head", EPI_GELU_F32, e->g_dense, e->m_hs, e->m_wdense, gp(rows, d, d, e->b_dense, e->g, d)));
+  const bool esm1 = c.arch == PGIBBS_ARCH_ESM1;
+  if (esm1) {  // logits = embed_out . x + embed_out_bias: no final LayerNorm, no dense / GELU / LayerNorm head
+    TRY(run_gather_f32(e, e->x, e->g, rows, sched, iter));
+  } else {
+    TRY(run_ln(e, e->x, raw_get(e, "emb_layer_norm_after.weight", -1), raw_get(e, "emb_layer_norm_after.bias", -1),
+               e->hs, rows, &sched, iter));
+    TRY(run_gemm(e, "gemm_head", EPI_GELU_F32, e->g_dense, e->m_hs, e->m_wdense, gp(rows, d, d, e->b_dense, e->g, d)));
+  }
   {
     HeadParams p{};
     p.g = e->g;
-    p.ln_w = raw_get(e, "lm_head.layer_norm.weight", -1);
-    p.ln_b = raw_get(e, "lm_head.layer_norm.bias", -1);
-    p.emb = raw_get(e, "embed_tokens.weight", -1);
-    p.out_bias = raw_get(e, "lm_head.bias", -1);
+    p.no_ln = esm1;
+    p.ln_w = esm1 ? nullptr : raw_get(e, "lm_head.layer_norm.weight", -1);
+    p.ln_b = esm1 ? nullptr : raw_get(e, "lm_head.layer_norm.bias", -1);
+    p.emb = raw_get(e, esm1 ? "embed_out" : "embed_tokens.weight", -1);
+    p.out_bias = raw_get(e, esm1 ? "embed_out_bias" : "lm_head.bias", -1);
     p.logits_out = logits_out;
     p.tokens = sample ? e->tokens : nullptr;
-    p.rows = rows; p.d = d; p.V = c.vocab; p.T = e->T; p.eps = 1e-5f;
+    p.rows = rows; p.d = d; p.V = c.vocab; p.T = e->T; p.eps = e->ln_eps;
     p.sched = sched; p.iter = iter;
     p.valid_ids = e->valid_dev; p.n_valid = n_valid; p.top_k = k_eff; p.temperature = temperature;
     p.noise = (sample && e->noise) ? e->noise + static_cast<int64_t>(iter) * rows * e->noise_stride : nullptr;
@@ -802,6 +831,10 @@ int pgibbs_create(const pgibbs_model_config* cfg, int32_t device_id, pgibbs_engi
   pgibbs_engine* e = new pgibbs_engine();
   e->cfg = *cfg;
   e->device = device_id;
+  if (cfg->arch == PGIBBS_ARCH_ESM1) {  // ESM1LayerNorm eps, embed_scale = sqrt(embed_dim)
+    e->ln_eps = 1e-12f;
+    e->embed_scale = sqrtf(static_cast<float>(cfg->embed_dim));
+  }
   if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete e;
     return fail("cudaStreamCreate failed");
@@ -860,14 +893,21 @@ int pgibbs_finalize_weights(pgibbs_engine* e) {
   const auto& c = e->cfg;
   const int64_t d = c.embed_dim, F = c.ffn_dim, V = c.vocab;
   if (!raw_get(e, "embed_tokens.weight", V * d)) return 1;
-  if (c.arch != PGIBBS_ARCH_ESM2) {
-    if (!raw_get(e, "embed_positions.weight", (c.max_positions + 2) * d)) return 1;
-    if (!raw_get(e, "emb_layer_norm_before.weight", d) || !raw_get(e, "emb_layer_norm_before.bias", d)) return 1;
+  const bool esm1 = c.arch == PGIBBS_ARCH_ESM1;
+  if (esm1) {
+    // sinusoidal table (rows 2.. = positions 0..) with one spare row for the bias key/value slot; untied output
+    if (!raw_get(e, "embed_positions.weight", (c.max_positions + 3) * d)) return 1;
+    if (!raw_get(e, "embed_out", V * d) || !raw_get(e, "embed_out_bias", V)) return 1;
+  } else {
+    if (c.arch != PGIBBS_ARCH_ESM2) {
+      if (!raw_get(e, "embed_positions.weight", (c.max_positions + 2) * d)) return 1;
+      if (!raw_get(e, "emb_layer_norm_before.weight", d) || !raw_get(e, "emb_layer_norm_before.bias", d)) return 1;
+    }
+    if (c.arch == PGIBBS_ARCH_MSA && !raw_get(e, "msa_position_embedding", 1024 * d)) return 1;
+    if (!raw_get(e, "emb_layer_norm_after.weight", d) || !raw_get(e, "emb_layer_norm_after.bias", d)) return 1;
+    if (!raw_get(e, "lm_head.layer_norm.weight", d) || !raw_get(e, "lm_head.layer_norm.bias", d)) return 1;
+    if (!raw_get(e, "lm_head.bias", V)) return 1;
   }
-  if (c.arch == PGIBBS_ARCH_MSA && !raw_get(e, "msa_position_embedding", 1024 * d)) return 1;
-  if (!raw_get(e, "emb_layer_norm_after.weight", d) || !raw_get(e, "emb_layer_norm_after.bias", d)) return 1;
-  if (!raw_get(e, "lm_head.layer_norm.weight", d) || !raw_get(e, "lm_head.layer_norm.bias", d)) return 1;
-  if (!raw_get(e, "lm_head.bias", V)) return 1;
   e->L.resize(c.layers);
   for (int i = 0; i < c.layers; ++i) {
     LayerW& l = e->L[i];
@@ -885,6 +925,7 @@ int pgibbs_finalize_weights(pgibbs_engine* e) {
     TRY(pack_linear(e, ffn + "fc2", d, F, &l.w2, &l.b2));
     if (!(l.ln1w = raw_get(e, ln1 + ".weight", d)) || !(l.ln1b = raw_get(e, ln1 + ".bias", d))) return 1;
     if (!(l.ln2w = raw_get(e, ln2 + ".weight", d)) || !(l.ln2b = raw_get(e, ln2 + ".bias", d))) return 1;
+    if (esm1 && (!(l.bias_k = raw_get(e, attn + "bias_k", d)) || !(l.bias_v = raw_get(e, attn + "bias_v", d)))) return 1;
     if (c.arch == PGIBBS_ARCH_MSA) {
       const std::string ca = p + "column_self_attention.layer.", cl = p + "column_self_attention.layer_norm";
       TRY(pack_qkv(e, ca, &l.c_wqkv, &l.c_bqkv));
@@ -900,9 +941,11 @@ int pgibbs_finalize_weights(pgibbs_engine* e) {
     drop_raw(e, ffn + "fc1.weight");
     drop_raw(e, ffn + "fc2.weight");
   }
-  TRY(pack_linear(e, "lm_head.dense", d, d, &e->w_dense, &e->b_dense));
-  CK(cudaStreamSynchronize(e->stream));
-  drop_raw(e, "lm_head.dense.weight");
+  if (!esm1) {
+    TRY(pack_linear(e, "lm_head.dense", d, d, &e->w_dense, &e->b_dense));
+    CK(cudaStreamSynchronize(e->stream));
+    drop_raw(e, "lm_head.dense.weight");
+  }
   e->finalized = true;
   return 0;
 }
@@ -919,7 +962,14 @@ int pgibbs_set_tokens(pgibbs_engine* e, const int32_t* tokens, int32_t B, int32_
       return fail("<pad> token at flat index %zu: padded batches are not on the Gibbs path and are not supported", i);
   }
   TRY(ensure_shape(e, B, R, T));
-  CK(cudaMemcpyAsync(e->tokens, host.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+  if (e->T != T) {  // ESM-1: one extra row per sequence (bias key/value slot); its token only feeds ignored rows
+    std::vector<int32_t> padded(static_cast<size_t>(e->M), e->cfg.cls_idx);
+    for (int sq = 0; sq < B * R; ++sq)
+      std::copy(host.begin() + static_cast<size_t>(sq) * T, host.begin() + static_cast<size_t>(sq + 1) * T,
+                padded.begin() + static_cast<size_t>(sq) * e->T);
+    host.swap(padded);
+  }
+  CK(cudaMemcpyAsync(e->tokens, host.data(), host.size() * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   return 0;
 }
@@ -927,7 +977,10 @@ int pgibbs_set_tokens(pgibbs_engine* e, const int32_t* tokens, int32_t B, int32_
 int pgibbs_get_tokens(pgibbs_engine* e, int32_t* tokens_out) {
   TRY(check_ready(e));
   if (!e->tokens || !tokens_out) return fail("no tokens resident or null output");
-  CK(cudaMemcpyAsync(tokens_out, e->tokens, static_cast<size_t>(e->M) * sizeof(int32_t), cudaMemcpyDefault, e->stream));
+  // [n_seq, Tu] out of the device's [n_seq, T] rows (T = Tu except for ESM-1's extra slot)
+  CK(cudaMemcpy2DAsync(tokens_out, static_cast<size_t>(e->Tu) * sizeof(int32_t), e->tokens,
+                       static_cast<size_t>(e->T) * sizeof(int32_t), static_cast<size_t>(e->Tu) * sizeof(int32_t),
+                       static_cast<size_t>(e->n_seq), cudaMemcpyDefault, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   TRY(prof_flush(e));
   return 0;
@@ -938,13 +991,13 @@ int pgibbs_set_schedule(pgibbs_engine* e, const int32_t* positions, int64_t nume
   TRY(check_ready(e));
   if (!e->tokens) return fail("set tokens before the schedule");
   if (!positions || numel <= 0 || n_iters <= 0 || P <= 0) return fail("invalid schedule");
-  if (P > e->T) return fail("P=%d exceeds the sequence length %d", P, e->T);
+  if (P > e->Tu) return fail("P=%d exceeds the sequence length %d", P, e->Tu);
   if (chain_stride < 0 || iter_stride < 0) return fail("negative schedule stride");
   if (static_cast<int64_t>(n_iters - 1) * iter_stride + P > numel) return fail("schedule buffer too small");
   std::vector<int32_t> host(numel);
   CK(cudaMemcpy(host.data(), positions, numel * sizeof(int32_t), cudaMemcpyDefault));
   for (int64_t i = 0; i < numel; ++i)
-    if (host[i] < 0 || host[i] >= e->T) return fail("scheduled position %d outside [0,%d)", host[i], e->T);
+    if (host[i] < 0 || host[i] >= e->Tu) return fail("scheduled position %d outside [0,%d)", host[i], e->Tu);
   CK(cudaStreamSynchronize(e->stream));
   if (e->positions_numel < numel) {
     if (e->positions) cudaFree(e->positions);
@@ -1000,7 +1053,7 @@ int pgibbs_forward_logits(pgibbs_engine* e, const int32_t* tokens, int32_t B, in
   if (!logits_out) return fail("null logits_out");
   Schedule s{e->identity_pos, 0, 0, T, 1, 0};
   TRY(forward(e, s, e->n_seq, 0, false, 0, -1.f, 0, e->logits));
-  CK(cudaMemcpyAsync(logits_out, e->logits, static_cast<size_t>(e->M) * e->cfg.vocab * sizeof(float),
+  CK(cudaMemcpyAsync(logits_out, e->logits, static_cast<size_t>(e->n_seq) * T * e->cfg.vocab * sizeof(float),
                      cudaMemcpyDefault, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   TRY(prof_flush(e));

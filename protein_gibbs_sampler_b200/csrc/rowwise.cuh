@@ -59,6 +59,7 @@ struct EmbedParams {
   int n_seq, T, d, rows_per_msa;
   int mask_idx, token_dropout;
   float eps;
+  float scale;             // embedding scale (sqrt(d) for ESM-1, else 1)
 };
 
 __global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
     const int i = lane + k * 32;
     if (i < nvec) {
       float4 a = zero ? make_float4(0, 0, 0, 0) : __ldg(e + i);
+      if (p.scale != 1.0f) { a.x *= p.scale; a.y *= p.scale; a.z *= p.scale; a.w *= p.scale; }
       if (p.token_dropout) {
         // x * (1 - 0.15*0.8) / (1 - ratio): multiply then divide, in fair-esm's order
         const float num = 0.88f;
@@ -153,6 +155,7 @@ struct LnParams {
   // gather (positions == nullptr -> identity)
   Schedule sched;
   int iter, T;
+  int identity;    // copy the (gathered) rows without normalising (ESM-1 has no final LayerNorm)
 };
 
 // VPL = float4 vectors held per lane (>= ceil(d / 128)): sized to the model so that the row fits in few registers
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(256, VPL <= 10 ? 4 : 2) layernorm_kernel(LnPar
       sum += v[k].x + v[k].y + v[k].z + v[k].w;
     }
   }
-  const float mean = warp_sum(sum) / p.d;
+  float mean = warp_sum(sum) / p.d;
   float sq = 0.f;
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
@@ -193,14 +196,17 @@ __global__ void __launch_bounds__(256, VPL <= 10 ? 4 : 2) layernorm_kernel(LnPar
             (a.w - mean) * (a.w - mean);
     }
   }
-  const float rstd = 1.0f / sqrtf(warp_sum(sq) / p.d + p.eps);
+  float rstd = 1.0f / sqrtf(warp_sum(sq) / p.d + p.eps);
+  if (p.identity) { mean = 0.f; rstd = 1.f; }
   const float4* w = reinterpret_cast<const float4*>(p.w);
   const float4* b = reinterpret_cast<const float4*>(p.b);
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     const int i = lane + k * 32;
     if (i < nvec) {
-      const float4 a = v[k], g = __ldg(w + i), h = __ldg(b + i);
+      const float4 a = v[k];
+      const float4 g = p.identity ? make_float4(1.f, 1.f, 1.f, 1.f) : __ldg(w + i);
+      const float4 h = p.identity ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(b + i);
       const float y0 = (a.x - mean) * rstd * g.x + h.x, y1 = (a.y - mean) * rstd * g.y + h.y;
       const float y2 = (a.z - mean) * rstd * g.z + h.z, y3 = (a.w - mean) * rstd * g.w + h.w;
       if constexpr (OUT_F16) {
@@ -213,6 +219,20 @@ __global__ void __launch_bounds__(256, VPL <= 10 ? 4 : 2) layernorm_kernel(LnPar
       }
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ESM-1 `add_bias_kv`: every sequence has one extra key/value slot (the row after its last token) whose k and v are
+// the layer's learned bias_k / bias_v (fair-esm MultiheadAttention: k = cat([k, bias_k]), v = cat([v, bias_v])).
+// ---------------------------------------------------------------------------------------------
+__global__ void bias_kv_kernel(__half* __restrict__ qkv, const float* __restrict__ bias_k,
+                               const float* __restrict__ bias_v, int n_seq, int T, int d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_seq * d) return;
+  const int seq = i / d, c = i % d;
+  __half* row = qkv + (static_cast<long long>(seq) * T + (T - 1)) * 3 * d;
+  row[d + c] = __float2half_rn(bias_k[c]);
+  row[2 * d + c] = __float2half_rn(bias_v[c]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -348,6 +368,7 @@ struct HeadParams {
   int noise_stride;
   unsigned long long seed;   // device RNG otherwise
   int emb_in_smem;
+  int no_ln;                 // project g as it is (ESM-1: logits = embed_out . x + bias, no LM-head LayerNorm)
   int skip_dup_writes;       // schedule may contain duplicate positions: last slot wins, like the reference loop
 };
 
@@ -391,7 +412,7 @@ __global__ void __launch_bounds__(256) head_sample_kernel(HeadParams p) {
 #pragma unroll
     for (int k = 0; k < kMaxVecPerLane; ++k) {
       const int i = lane + k * 32;
-      if (i < nvec) {
+      if (i < nvec && !p.no_ln) {
         const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_w) + i);
         const float4 h = __ldg(reinterpret_cast<const float4*>(p.ln_b) + i);
         float4 a = v[k];

@@ -8,7 +8,7 @@ import torch
 from . import _lib
 from ._lib import EngineError, check
 
-_ARCH = {"roberta_large": 0, "esm2": 1, "msa_transformer": 2}
+_ARCH = {"roberta_large": 0, "esm2": 1, "msa_transformer": 2, "esm1": 3}
 INT64_MAX = (1 << 63) - 1
 
 
@@ -59,6 +59,13 @@ class Engine:
                 continue  # tied to embed_tokens.weight (RobertaLMHead)
             t = t.detach().to(torch.float32).contiguous()
             check(self.lib.pgibbs_load_weight(self.h, name.encode(), _ptr(t), t.numel()))
+        if self.cfg["arch"] == "esm1":
+            # sinusoidal positions are a fixed table: computed here exactly as fair-esm does (float32) and handed to
+            # the engine through the learned-position slot (rows 2.. are positions 0.., one spare row for the
+            # internal bias-key/value slot)
+            from .weights import sinusoidal_table
+            tbl = sinusoidal_table(self.cfg["max_positions"] + 3, self.cfg["embed_dim"]).contiguous()
+            check(self.lib.pgibbs_load_weight(self.h, b"embed_positions.weight", _ptr(tbl), tbl.numel()))
         check(self.lib.pgibbs_finalize_weights(self.h))
 
     # ---- state

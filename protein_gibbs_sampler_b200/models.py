@@ -1,8 +1,8 @@
 """Model triples (``.model`` / ``.alphabet`` / ``.batch_converter``) the samplers consume.
 
 Same contract as /root/reference/src/pgen/models.py:59-88 (stated at esm_sampler.py:55-57), but ``.model``
-is a handle on the CUDA engine instead of a fair-esm ``nn.Module``.  ESM1b / ESM1v / ESM_MSA1 keep the
-reference's class names; ESM2_t6_8M / ESM2_t30_150M / ESM2_t33_650M are additions (BASELINE configs 1 and 4).
+is a handle on the CUDA engine instead of a fair-esm ``nn.Module``.  ESM1b / ESM1v / ESM6 / ESM12 / ESM34 / ESM_MSA1
+keep the reference's class names; ESM2_t6_8M / ESM2_t30_150M / ESM2_t33_650M are additions (BASELINE configs 1 and 4).
 
 No pretrained checkpoint can be downloaded in this environment: by default the weights are seeded synthetic
 tensors (``weights.synthetic_state_dict``).  Pass ``checkpoint=<path to a fair-esm .pt>`` or
@@ -96,6 +96,21 @@ class ESM1v(_Triple):
     config_name = "esm1v_t33_650M_UR90S_1"
 
 
+class ESM6(_Triple):
+    config_name = "esm1_t6_43M_UR50S"
+    alphabet_factory = staticmethod(Alphabet.esm1)
+
+
+class ESM12(_Triple):
+    config_name = "esm1_t12_85M_UR50S"
+    alphabet_factory = staticmethod(Alphabet.esm1)
+
+
+class ESM34(_Triple):
+    config_name = "esm1_t34_670M_UR50S"
+    alphabet_factory = staticmethod(Alphabet.esm1)
+
+
 class ESM2_t6_8M(_Triple):
     config_name = "esm2_t6_8M_UR50D"
 
@@ -118,7 +133,7 @@ class CustomModel(_Triple):
 
     def __init__(self, cfg, state_dict=None, seed=0):
         self.cfg = dict(cfg)
-        self.alphabet = Alphabet.msa() if cfg["arch"] == "msa_transformer" else Alphabet.esm1b()
+        self.alphabet = {"msa_transformer": Alphabet.msa, "esm1": Alphabet.esm1}.get(cfg["arch"], Alphabet.esm1b)()
         if state_dict is None:
             state_dict = synthetic_state_dict(self.cfg, seed)
         self.model = EngineModule(self.cfg, self.alphabet, state_dict)

@@ -43,13 +43,35 @@ def synthetic_state_dict(cfg, seed=0, std=0.02, ln_noise=0.02, bias_std=0.02):
         else:
             for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):
                 lin(p + "self_attn." + nm, d, d)
+            if cfg["arch"] == "esm1":  # add_bias_kv=True: one learned extra key / value per layer
+                sd[p + "self_attn.bias_k"] = torch.randn(1, 1, d, generator=g) * std * 5
+                sd[p + "self_attn.bias_v"] = torch.randn(1, 1, d, generator=g) * std * 5
             ln(p + "self_attn_layer_norm")
             lin(p + "fc1", F, d)
             lin(p + "fc2", d, F)
             ln(p + "final_layer_norm")
+    if cfg["arch"] == "esm1":  # untied output projection straight from the last layer
+        sd["embed_out"] = torch.randn(V, d, generator=g) * std * 5
+        sd["embed_out_bias"] = torch.randn(V, generator=g) * bias_std
+        return sd
     ln("emb_layer_norm_after")
     lin("lm_head.dense", d, d)
     ln("lm_head.layer_norm")
     sd["lm_head.weight"] = sd["embed_tokens.weight"]  # tied (RobertaLMHead)
     sd["lm_head.bias"] = torch.randn(V, generator=g) * bias_std
     return sd
+
+
+def sinusoidal_table(num_embeddings, dim, padding_idx=1):
+    """fair-esm SinusoidalPositionalEmbedding.get_embedding (esm/modules.py), float32 like the original: row p is
+    [sin(p f_0..) | cos(p f_0..)], f_j = exp(-j ln(10000) / (dim/2 - 1)); the padding row is zero."""
+    import math
+    half = dim // 2
+    step = math.log(10000) / (half - 1)
+    freq = torch.exp(torch.arange(half, dtype=torch.float) * -step)
+    ang = torch.arange(num_embeddings, dtype=torch.float).unsqueeze(1) * freq.unsqueeze(0)
+    tbl = torch.cat([torch.sin(ang), torch.cos(ang)], dim=1).view(num_embeddings, -1)
+    if dim % 2 == 1:
+        tbl = torch.cat([tbl, torch.zeros(num_embeddings, 1)], dim=1)
+    tbl[padding_idx, :] = 0
+    return tbl

@@ -106,13 +106,15 @@ def test_generate_step_golden_and_statistics(golden):
 def _tokens(cfg, shape, seed):
     g = torch.Generator().manual_seed(seed)
     tok = torch.randint(4, 24, shape, generator=g)
-    tok[..., 0] = 0
-    if cfg["arch"] != "msa_transformer":
+    esm1 = cfg["arch"] == "esm1"
+    cls, mask = (32, 33) if esm1 else (0, 32)
+    tok[..., 0] = cls
+    if cfg["arch"] not in ("msa_transformer", "esm1"):
         tok[..., -1] = 2
     flat = tok.view(-1, shape[-1])
-    flat[0, 3:9] = 32
+    flat[0, 3:9] = mask
     if flat.shape[0] > 1:
-        flat[1, 1:shape[-1] - 1] = 32       # a fully masked chain: largest token-dropout rescale
+        flat[1, 1:shape[-1] - 1] = mask     # a fully masked chain: largest token-dropout rescale
     return tok
 
 
@@ -122,6 +124,9 @@ def _tokens(cfg, shape, seed):
     ("roberta_large", 3, 256, 4, 512, (3, 130)), ("esm2", 2, 640, 20, 2560, (2, 70)),
     ("roberta_large", 33, 1280, 20, 5120, (2, 66)),         # full-depth ESM-1b (config 2/5 model)
     ("esm2", 33, 1280, 20, 5120, (2, 40)),                  # full-depth ESM-2 650M (config 4 model)
+    ("esm1", 2, 128, 2, 256, (2, 24)), ("esm1", 2, 128, 8, 256, (3, 131)),  # ESM-1: head_dim 64 / 16, bias key/value
+    ("esm1", 6, 768, 12, 3072, (2, 66)),                    # esm1_t6_43M geometry (the reference's esm6)
+    ("esm1", 2, 256, 4, 512, (2, 257)),                     # 257 tokens + the bias slot = 258: tcgen05 attention tail
     ("msa_transformer", 2, 128, 2, 256, (2, 4, 17)), ("msa_transformer", 2, 768, 12, 3072, (1, 8, 33)),
     ("msa_transformer", 2, 128, 2, 256, (2, 1, 9)),         # single-row MSA (pgen_msa_revised --alignment_size 1)
     ("msa_transformer", 2, 128, 2, 256, (1, 3, 200)),       # tcgen05 tied row attention, two query tiles
@@ -276,3 +281,22 @@ def test_generate_single_batch_equals_sequential_calls():
         got = s.generate_single_batch(msa, 3, **kw)
         assert got == want, (kw, got, want)
         assert len(set(want)) > 1 or kw["k"] == 1   # the chains really are different draws
+
+
+def test_esm1_generate_matches_oracle_loop():
+    """ESM-1 family end to end (the reference's esm6 / esm12 / esm34): replay mode against the oracle port of the
+    reference loop on the ESM-1 oracle model, same seeds -> same position schedule; residues may differ only where
+    a draw sits inside the logit error band."""
+    from oracle.fair_esm import OracleModel
+    from oracle.gibbs_loop import esm_generate
+    from protein_gibbs_sampler_b200.config import tiny_config
+    cfg = tiny_config("esm1", 2, 128, 2, 256)
+    s, sd = make(cfg, 11)
+    kw = dict(seed_seq="MKTAYIAKQRQISFVKSHFSRQ", batch_size=3, num_iters=3, top_k=3, burnin=1, num_positions=5)
+    random.seed(3); torch.manual_seed(3)
+    want = esm_generate(OracleModel(cfg, sd), 3, **kw)
+    random.seed(3); torch.manual_seed(3)
+    got = s.generate(3, show_progress_bar=False, **kw)
+    assert len(got) == 3 and all(len(x) == 22 and set(x) <= set("ACDEFGHIKLMNPQRSTVWY") for x in got)
+    diff = sum(a != b for x, y in zip(got, want) for a, b in zip(x, y))
+    assert diff <= 2, (got, want)

@@ -212,3 +212,17 @@ def test_untokenize(sampler, msa_sampler):
 def test_upgrade_state_dict_strips_fair_esm_prefixes():
     sd = {"encoder.sentence_encoder.layers.0.fc1.weight": 1, "encoder.lm_head.bias": 2, "msa.embed_tokens.weight": 3}
     assert set(models.upgrade_state_dict(sd)) == {"layers.0.fc1.weight", "lm_head.bias", "embed_tokens.weight"}
+
+
+def test_esm1_alphabet_ids_pinned_by_reference_fixtures():
+    """ESM-1 alphabet (esm6 / esm12 / esm34): <cls>=32, <mask>=33, A=5 (`/root/reference/test/test_esm_sampler.py:43-66`),
+    bos only, 35 tokens; identical to the oracle's restatement of `esm.data.Alphabet.from_architecture("ESM-1")`."""
+    from oracle.fair_esm import Alphabet as OracleAlphabet
+    from protein_gibbs_sampler_b200.alphabet import Alphabet
+    a = Alphabet.esm1()
+    assert (len(a), a.cls_idx, a.mask_idx, a.get_idx("A"), a.padding_idx, a.get_idx("<sep>")) == (35, 32, 33, 5, 1, 34)
+    assert a.prepend_bos and not a.append_eos
+    assert a.all_toks == OracleAlphabet.from_architecture("ESM-1").all_toks
+    toks = a.get_batch_converter()([("0", "AA<mask>")])[2]
+    assert toks.tolist() == [[32, 5, 5, 33]]
+    assert sorted(a.get_idx(t) for t in "ACDEFGHIKLMNPQRSTVWY") == list(range(4, 24))
