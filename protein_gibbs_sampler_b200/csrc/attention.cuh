@@ -7,8 +7,9 @@
 // No padding mask: the Gibbs path never contains <pad>.
 // Replaces fair-esm MultiheadAttention's bmm/softmax/bmm (call site /root/reference/src/pgen/esm_sampler.py:223).
 //
-// v1 uses the warp-level mma.sync.m16n8k16 path (attention is 3-12 % of the step's FLOPs); the tcgen05
-// version is tracked in DESIGN.md.
+// Warp-level mma.sync.m16n8k16 path.  The production path for head_dim 64 sequence attention is the tcgen05 kernel in
+// attention_fa.cuh; this kernel serves head_dim 16 / 32 (ESM-2 8M / 150M), MSA column attention (strided token
+// mapping, at most a few dozen keys per group) and 9..16 trailing query rows left over by the tcgen05 kernel.
 #pragma once
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>

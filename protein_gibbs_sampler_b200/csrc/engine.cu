@@ -15,7 +15,6 @@
 
 #include "../../include/pgibbs.h"
 #include "attention.cuh"
-#include "attention_tc.cuh"
 #include "attention_fa.cuh"
 #include "gemm.cuh"
 #include "msa_attention.cuh"
@@ -547,33 +546,20 @@ static int launch_attention(const AttnParams& p, int groups, int H, int hd, cuda
 }
 
 // head_dim 64 sequence attention runs on tcgen05 (attention_fa.cuh); everything else keeps the mma.sync kernel.
-// PGIBBS_ATTN=legacy selects the mma.sync kernel, PGIBBS_ATTN=tc1 the first-generation one-tile-per-CTA tcgen05
-// kernel (both kept for A/B measurements).  PGIBBS_ATTN_TAIL=0 makes the tcgen05 kernel also process a nearly
-// empty last query tile itself instead of handing the few trailing rows (T % 128 <= 16) to the mma.sync kernel.
+// PGIBBS_ATTN=legacy selects the mma.sync kernel for A/B measurements.  PGIBBS_ATTN_TAIL: 1 (default) trailing rows
+// (T % 128 <= 8) on the kernel's tail warp, 2 on a second mma.sync launch, 0 as a partly filled tile.
 static unsigned long long* g_fa_trace = nullptr;  // device buffer for the attention timeline (debug)
-static int g_attn_mode = -1;  // 0 legacy, 1 tc1, 2 fa
+static int g_attn_mode = -1;  // 0 legacy, 2 fa
 static int g_attn_tail = 1;
 static int g_attn_stagger = 600;  // PGIBBS_ATTN_STAGGER (cycles)
 static int attn_mode(int hd) {
   if (g_attn_mode < 0) {
     const char* v = getenv("PGIBBS_ATTN");
-    g_attn_mode = (v && !strcmp(v, "tc1")) ? 1 : (v && !strcmp(v, "legacy")) ? 0 : 2;
+    g_attn_mode = (v && !strcmp(v, "legacy")) ? 0 : 2;
     if (const char* t = getenv("PGIBBS_ATTN_TAIL")) g_attn_tail = atoi(t);
     if (const char* t = getenv("PGIBBS_ATTN_STAGGER")) g_attn_stagger = atoi(t);
   }
   return hd == 64 ? g_attn_mode : 0;
-}
-static int launch_attention_tc(const CUtensorMap& qkv3, __half* ctx, int n_seq, int T, int H, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    CK(cudaFuncSetAttribute(attention_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes));
-    configured = true;
-  }
-  AttnTcParams p{ctx, T, H * 64, H * 64};
-  dim3 grid((T + 127) / 128, H, n_seq);
-  attention_tcgen05_kernel<<<grid, kAtThreads, kAtSmemBytes, st>>>(qkv3, p);
-  CK(cudaGetLastError());
-  return 0;
 }
 // qkv: fused activation [n_seq*T, 3*H*64]; ctx: [n_seq*T, H*64].
 static int launch_attention_fa(const CUtensorMap& qkv3, const CUtensorMap& ctx3, const __half* qkv, __half* ctx,
@@ -633,7 +619,6 @@ static int run_attention(pgibbs_engine* e) {
   ProfScope ps(e, "attention");
   const int mode = attn_mode(hd);
   if (mode == 2) return launch_attention_fa(e->m_qkv3, e->m_ctx3, e->qkv, e->ctx, e->n_seq, e->T, H, e->stream);
-  if (mode == 1) return launch_attention_tc(e->m_qkv3, e->ctx, e->n_seq, e->T, H, e->stream);
   AttnParams p{e->qkv, e->ctx, e->T, 3 * d, d, d, 2 * d, 1, 0, 1, e->T};
   return launch_attention(p, e->n_seq, H, hd, e->stream);
 }
@@ -1237,7 +1222,6 @@ int pgibbs_op_attention(int32_t device_id, const float* qkv, float* ctx, int32_t
     }
     auto launch = [&]() -> int {
       if (mode == 2) return launch_attention_fa(m3, c3, d16, c16, n_seq, T, heads, nullptr);
-      if (mode == 1) return launch_attention_tc(m3, c16, n_seq, T, heads, nullptr);
       AttnParams p{d16, c16, T, 3 * d, d, d, 2 * d, 1, 0, 1, T};
       return launch_attention(p, n_seq, heads, head_dim, nullptr);
     };
