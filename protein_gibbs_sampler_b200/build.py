@@ -26,7 +26,8 @@ def build_library(force=False, verbose=False):
     if not force and not is_stale():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", OUT, os.path.join(CSRC, "engine.cu")]
+    extra = os.environ.get("PGIBBS_NVCC_EXTRA", "").split()   # e.g. -DPGIBBS_FA_POLY_EVERY=3 for kernel A/B builds
+    cmd = [nvcc] + NVCC_FLAGS + extra + ["-o", OUT, os.path.join(CSRC, "engine.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     log = r.stdout + r.stderr
     with open(os.path.join(HERE, "build.log"), "w") as f:
