@@ -487,13 +487,13 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
           auto chunk = [&](auto wtag) {
             constexpr int W = decltype(wtag)::value;
             float v[W];
+            {
+              uint32_t r[W];  // both 32-column loads in flight before the single wait
 #pragma unroll
-            for (int g = 0; g < W / 32; ++g) {
-              uint32_t r[32];
-              tmem_ld32(tSb + g * 32, r);
+              for (int g = 0; g < W / 32; ++g) tmem_ld32(tSb + g * 32, reinterpret_cast<uint32_t(&)[32]>(r[g * 32]));
               tmem_wait_ld();
 #pragma unroll
-              for (int c = 0; c < 32; ++c) v[g * 32 + c] = __uint_as_float(r[c]);
+              for (int c = 0; c < W; ++c) v[c] = __uint_as_float(r[c]);
             }
             if (rem < W) {                                // sequence edge: keys >= T do not exist
 #pragma unroll
@@ -540,31 +540,24 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       trace(0x23);  // O complete
       uint8_t* stage = sQ + (qs * 2 + t) * kFaTile;
       if (warp_live) {
-        float inv;
-        {
-          uint32_t ls[16];
-          tmem_ld16(tO + 64, ls);
-          tmem_wait_ld();
-          inv = 1.0f / __uint_as_float(ls[0]);
-        }
+        uint32_t ls[16], o[64];  // row sum and both halves of O in flight before the single wait
+        tmem_ld16(tO + 64, ls);
+        tmem_ld32(tO, reinterpret_cast<uint32_t(&)[32]>(o[0]));
+        tmem_ld32(tO + 32, reinterpret_cast<uint32_t(&)[32]>(o[32]));
+        tmem_wait_ld();
+        const float inv = 1.0f / __uint_as_float(ls[0]);
         const int r = quad * 32 + lane;
         uint8_t* rowp = stage + r * 128;
 #pragma unroll
-        for (int hlf = 0; hlf < 2; ++hlf) {
-          uint32_t o[32];
-          tmem_ld32(tO + hlf * 32, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 w;
-            __half2 h0 = __floats2half2_rn(__uint_as_float(o[8 * q]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
-            __half2 h1 = __floats2half2_rn(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
-            __half2 h2 = __floats2half2_rn(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
-            __half2 h3 = __floats2half2_rn(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
-            w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
-            w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(rowp + (((hlf * 4 + q) ^ (r & 7)) << 4)) = w;  // 128B swizzle, matches tmCtx
-          }
+        for (int q = 0; q < 8; ++q) {
+          uint4 w;
+          __half2 h0 = __floats2half2_rn(__uint_as_float(o[8 * q]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
+          __half2 h1 = __floats2half2_rn(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
+          __half2 h2 = __floats2half2_rn(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
+          __half2 h3 = __floats2half2_rn(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
+          w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
+          w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+          *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) << 4)) = w;  // 128B swizzle, matches tmCtx
         }
       }
       tc_fence_before();
