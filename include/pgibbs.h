@@ -67,6 +67,9 @@ int pgibbs_set_schedule(pgibbs_engine* e, const int32_t* positions, int64_t nume
 int pgibbs_set_noise(pgibbs_engine* e, const float* exp_noise, int64_t numel, int32_t stride);
 /* Device RNG (Philox4x32-10) used when no replay noise is set. */
 int pgibbs_set_device_rng(pgibbs_engine* e, uint64_t seed);
+/* Chains sharded across GPUs: global index of this engine's first chain, so that the device RNG draws for chain c of
+ * this shard what a single engine holding all chains would draw for chain first_chain + c. */
+int pgibbs_set_chain_offset(pgibbs_engine* e, int64_t first_chain);
 
 /* The loop body esm_sampler.py:209-234 (esm_msa_sampler.py:221-248) for iterations
  * [first_iter, first_iter + num_iters): <mask> scatter (if mask_flag) -> forward -> generate_step at every

@@ -34,6 +34,7 @@ SIGNATURES = {
     "pgibbs_set_schedule": (c_i32, [c_void_p, c_void_p, c_i64, c_i32, c_i32, c_i64, c_i64, c_i32]),
     "pgibbs_set_noise": (c_i32, [c_void_p, c_void_p, c_i64, c_i32]),
     "pgibbs_set_device_rng": (c_i32, [c_void_p, ctypes.c_uint64]),
+    "pgibbs_set_chain_offset": (c_i32, [c_void_p, c_i64]),
     "pgibbs_run": (c_i32, [c_void_p, c_i32, c_i32, c_i64, c_i32, c_f32, c_i32, c_void_p, c_i32]),
     "pgibbs_run_single": (c_i32, [c_void_p, c_i32, c_i32, c_i64, c_i32, c_f32, c_i32, c_i32, c_void_p, c_i32]),
     "pgibbs_forward_logits": (c_i32, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p]),

@@ -294,6 +294,7 @@ struct pgibbs_engine {
   int64_t noise_numel = 0;
   int noise_stride = 0;
   uint64_t seed = 0x243F6A8885A308D3ull;
+  int64_t rng_chain_offset = 0;  // global index of this engine's first chain (pgibbs_set_chain_offset)
   int32_t* valid_dev = nullptr;
   int32_t* identity_pos = nullptr;  // 0..T-1 (forward_logits)
   int layer_limit = -1;
@@ -723,6 +724,7 @@ static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int it
     p.noise = (sample && e->noise) ? e->noise + static_cast<int64_t>(iter) * rows * e->noise_stride : nullptr;
     p.noise_stride = e->noise_stride;
     p.seed = e->seed;
+    p.rng_row_offset = e->rng_chain_offset * sched.P;
     p.skip_dup_writes = e->has_dup;
     const size_t emb_bytes = static_cast<size_t>(c.vocab) * d * sizeof(float);
     p.emb_in_smem = emb_bytes <= 200 * 1024;
@@ -1012,6 +1014,13 @@ int pgibbs_set_noise(pgibbs_engine* e, const float* exp_noise, int64_t numel, in
 int pgibbs_set_device_rng(pgibbs_engine* e, uint64_t seed) {
   if (!e) return fail("null engine");
   e->seed = seed;
+  return 0;
+}
+
+int pgibbs_set_chain_offset(pgibbs_engine* e, int64_t first_chain) {
+  if (!e) return fail("null engine");
+  if (first_chain < 0) return fail("negative chain offset");
+  e->rng_chain_offset = first_chain;
   return 0;
 }
 

@@ -261,7 +261,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 __device__ __forceinline__ int generate_step_warp(float mine, float extra, int lane, int row, int iter,
                                                   const int32_t* __restrict__ valid_ids, int n, int k,
                                                   float temperature, const float* __restrict__ noise,
-                                                  int noise_stride, unsigned long long seed) {
+                                                  int noise_stride, unsigned long long seed,
+                                                  long long rng_row_offset = 0) {
   // Up to 64 candidates: lane holds candidate slots `lane` (a) and `lane + 32` (b).
   const bool has_a = lane < n, has_b = lane + 32 < n;
   const int id_a = has_a ? valid_ids[lane] : 0, id_b = has_b ? valid_ids[lane + 32] : 0;
@@ -296,7 +297,8 @@ __device__ __forceinline__ int generate_step_warp(float mine, float extra, int l
   const float denom = warp_sum(ea + eb);
   auto draw = [&](int rank) {
     if (noise) return noise[static_cast<long long>(row) * noise_stride + rank];
-    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(iter), static_cast<uint32_t>(row),
+    // the counter uses the GLOBAL row (this shard's first row + row) so that a sharded run draws what one GPU would
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(iter), static_cast<uint32_t>(row + rng_row_offset),
                                              static_cast<uint32_t>(rank), 0x5eedu),
                                   make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
     const float u = (static_cast<float>(r.x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
@@ -367,6 +369,7 @@ struct HeadParams {
   const float* noise;        // replay: [rows, noise_stride] Exp(1) draws for this iteration, slot j <-> j-th largest
   int noise_stride;
   unsigned long long seed;   // device RNG otherwise
+  long long rng_row_offset;  // global index of this engine's first sampled row (chains sharded across GPUs)
   int emb_in_smem;
   int no_ln;                 // project g as it is (ESM-1: logits = embed_out . x + bias, no LM-head LayerNorm)
   int skip_dup_writes;       // schedule may contain duplicate positions: last slot wins, like the reference loop
@@ -446,7 +449,7 @@ __global__ void __launch_bounds__(256) head_sample_kernel(HeadParams p) {
     if (!p.tokens) continue;
 
     const int best_id = generate_step_warp(mine, extra, lane, row, p.iter, p.valid_ids, p.n_valid, p.top_k,
-                                           p.temperature, p.noise, p.noise_stride, p.seed);
+                                           p.temperature, p.noise, p.noise_stride, p.seed, p.rng_row_offset);
     if (lane == 0) {
       const int chain = row / p.sched.P, slot = row % p.sched.P;
       const int32_t* plist = p.sched.positions + p.iter * p.sched.iter_stride + chain * p.sched.chain_stride;

@@ -107,6 +107,9 @@ class Engine:
     def set_device_rng(self, seed):
         check(self.lib.pgibbs_set_device_rng(self.h, ctypes.c_uint64(seed & ((1 << 64) - 1))))
 
+    def set_chain_offset(self, first_chain):
+        check(self.lib.pgibbs_set_chain_offset(self.h, int(first_chain)))
+
     @staticmethod
     def _burnin(b):
         """`ii < burnin` for integer ii  <=>  ii < ceil(burnin); inf -> never leave burn-in."""

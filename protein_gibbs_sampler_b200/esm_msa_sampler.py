@@ -45,6 +45,7 @@ class ESM_MSA_sampler():
         self.device, self.cuda = parse_device(device)
         self.model.model.to(self.device)
         self.valid_aa_idx = sorted(self.model.alphabet.get_idx(tok) for tok in ESM_MSA_ALLOWED_AMINO_ACIDS)
+        self.shard = None   # see ESM_sampler.shard / parallel.shard_sampler
         self.toks = [self.model.alphabet.get_tok(idx) for idx in self.valid_aa_idx]
 
     # ------------------------------------------------------------------ host helpers (reference API)
@@ -124,14 +125,43 @@ class ESM_MSA_sampler():
         return SchedulePlan(pos, num_iters, num_positions, n_chains * num_positions, num_positions, dup), last_i
 
     def run_plan(self, tokens, plan, top_k, temperature, burnin, mask):
-        """Run every iteration of one round on the GPU; returns the final tokens [B,R,C].  No CPU path."""
+        """Run every iteration of one round on the GPU; returns the final tokens [B,R,C].  No CPU path.
+        With ``self.shard`` set (parallel.shard_sampler) whole MSAs are split across ranks: schedule and replay noise
+        are drawn for all of them, this rank runs MSAs [lo, hi) and the final tokens are all-gathered."""
         engine = self.model.model.require_engine()
-        engine.set_tokens(tokens)
-        engine.set_schedule(plan.positions, plan.n_iters, plan.P, plan.iter_stride, plan.chain_stride,
-                            plan.has_duplicates)
-        self._noise(engine, plan.n_iters, tokens.shape[0] * tokens.shape[1] * plan.P, top_k, burnin)
-        engine.run(0, plan.n_iters, burnin, top_k, temperature, mask, self.valid_aa_idx)
-        return engine.get_tokens()
+        B, R = tokens.shape[0], tokens.shape[1]
+        n_chains = B * R
+        noise = stride = None
+        if self.rng == "replay":
+            noise, stride = draw_replay_noise(plan.n_iters, n_chains * plan.P, len(self.valid_aa_idx), top_k, burnin)
+        else:
+            device_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        lo, hi = 0, B
+        if self.shard is not None:
+            from .parallel import shard_range
+            rank, world, _ = self.shard
+            lo, hi = shard_range(B, world, rank)   # never split one MSA: its rows are coupled by the attention
+            if noise is not None:
+                noise = noise.reshape(plan.n_iters, n_chains, plan.P, stride)[:, lo * R:hi * R]
+                noise = noise.reshape(plan.n_iters, -1, stride)
+            plan, tokens = plan.slice_chains(lo * R, hi * R, n_chains), tokens[lo:hi]
+        if hi > lo:
+            engine.set_tokens(tokens)
+            engine.set_schedule(plan.positions, plan.n_iters, plan.P, plan.iter_stride, plan.chain_stride,
+                                plan.has_duplicates)
+            if noise is not None:
+                engine.set_noise(noise.contiguous(), stride)
+            else:
+                engine.set_noise(None)
+                engine.set_device_rng(device_seed)
+            engine.set_chain_offset(lo * R)
+            engine.run(0, plan.n_iters, burnin, top_k, temperature, mask, self.valid_aa_idx)
+            out = engine.get_tokens()
+        else:
+            out = torch.empty((0, R, tokens.shape[-1]), dtype=torch.int64)
+        if self.shard is not None:
+            out = torch.cat(self.shard[2](out), dim=0)
+        return out
 
     # ------------------------------------------------------------------ generate
     def generate(self, n_samples, seed_msa, batch_size=1, in_order=False, max_len=None, leader_length=0,

@@ -86,6 +86,13 @@ class SchedulePlan:
         o = it * self.iter_stride + chain * self.chain_stride
         return self.positions[o:o + self.P].tolist()
 
+    def slice_chains(self, lo, hi, n_chains):
+        """The plan of chains [lo, hi) out of n_chains (a shared list -- strides 0 -- is everybody's)."""
+        if self.chain_stride == 0:
+            return self
+        pos = self.positions.reshape(self.n_iters, n_chains, self.P)[:, lo:hi]
+        return SchedulePlan(pos, self.n_iters, self.P, (hi - lo) * self.P, self.P, self.has_duplicates)
+
 
 def draw_replay_noise(n_iters, rows, n_valid, top_k, burnin):
     """Exp(1) variates in the order the reference loop consumes them (iteration, chain, slot)."""
@@ -111,6 +118,10 @@ class ESM_sampler():
         self.model.model.to(self.device)
         self.valid_aa_idx = sorted(self.model.alphabet.get_idx(tok) for tok in ESM_ALLOWED_AMINO_ACIDS)
         self.last_timing = {}
+        # Chains sharded across GPUs (parallel.shard_sampler): (rank, world_size, all_gather) or None.  Every rank
+        # runs the same host code with the same RNG state, pre-draws the schedule (and replay noise) of ALL chains,
+        # runs its contiguous slice and gathers the final tokens, so the result equals the single-GPU run's.
+        self.shard = None
 
     # ------------------------------------------------------------------ host helpers (reference API)
     def untokenize_batch(self, batch, bos, eos):
@@ -218,20 +229,37 @@ class ESM_sampler():
         Raises if the model has no CUDA engine: there is no CPU path."""
         t0 = time.perf_counter()
         engine = self.model.model.require_engine()
-        engine.set_tokens(tokens)
-        engine.set_schedule(plan.positions, plan.n_iters, plan.P, plan.iter_stride, plan.chain_stride,
-                            plan.has_duplicates)
         n_chains = int(np.prod(tokens.shape[:-1]))
-        if self.rng == "replay":
+        noise = stride = None
+        if self.rng == "replay":   # drawn for ALL chains, in the reference's order, whatever the sharding
             noise, stride = draw_replay_noise(plan.n_iters, n_chains * plan.P, len(self.valid_aa_idx), top_k, burnin)
-            engine.set_noise(noise, stride)
         else:
-            engine.set_noise(None)
-            engine.set_device_rng(int(torch.randint(0, 2 ** 62, (1,)).item()))
+            device_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        lo, hi = 0, n_chains
+        if self.shard is not None:
+            from .parallel import shard_range
+            rank, world, _ = self.shard
+            lo, hi = shard_range(n_chains, world, rank)
+            if noise is not None:
+                noise = noise.reshape(plan.n_iters, n_chains, plan.P, stride)[:, lo:hi].reshape(plan.n_iters, -1, stride)
+            plan, tokens = plan.slice_chains(lo, hi, n_chains), tokens[lo:hi]
+        if hi > lo:
+            engine.set_tokens(tokens)
+            engine.set_schedule(plan.positions, plan.n_iters, plan.P, plan.iter_stride, plan.chain_stride,
+                                plan.has_duplicates)
+            if noise is not None:
+                engine.set_noise(noise.contiguous(), stride)
+            else:
+                engine.set_noise(None)
+                engine.set_device_rng(device_seed)
+            engine.set_chain_offset(lo)
         t1 = time.perf_counter()
-        engine.run(0, plan.n_iters, burnin, top_k, temperature, mask, self.valid_aa_idx)
+        if hi > lo:
+            engine.run(0, plan.n_iters, burnin, top_k, temperature, mask, self.valid_aa_idx)
         t2 = time.perf_counter()
-        out = engine.get_tokens()
+        out = engine.get_tokens() if hi > lo else torch.empty((0, 1, tokens.shape[-1]), dtype=torch.int64)
+        if self.shard is not None:
+            out = torch.cat(self.shard[2](out), dim=0)   # every rank ends up with all chains, in chain order
         t3 = time.perf_counter()
         # host-side trace of the last batch (the reference has no tracing; this is the engine's)
         self.last_timing = {"upload_s": t1 - t0, "enqueue_s": t2 - t1, "wait_and_download_s": t3 - t2}

@@ -31,3 +31,24 @@ def gather_sequences(local_seqs):
     bucket = [None] * dist.get_world_size()
     dist.all_gather_object(bucket, list(local_seqs))
     return [s for part in bucket for s in part]
+
+
+def all_gather_tokens(local):
+    """List of every rank's int64 token tensor [n_r, R, T] in rank order (ranks may hold different n_r, even 0)."""
+    bucket = [None] * dist.get_world_size()
+    dist.all_gather_object(bucket, local.cpu())
+    return bucket
+
+
+def shard_sampler(sampler, rank=None, world_size=None, all_gather=all_gather_tokens):
+    """Make ``sampler.generate`` run its chains sharded over the ranks of the default process group.
+
+    Every rank must call ``generate`` with the same arguments and the same ``random`` / ``torch`` RNG state (seed them
+    alike, or broadcast rank 0's state): each pre-draws the full position schedule (and, in replay mode, the Exp(1)
+    variates) in the reference's order, runs only its contiguous slice of chains on its own GPU -- no collective on the
+    iteration path -- and the final tokens are all-gathered once, so every rank returns the sequences a single GPU
+    would have produced.  ``all_gather`` is injectable for tests."""
+    if rank is None:
+        rank, world_size = dist.get_rank(), dist.get_world_size()
+    sampler.shard = (rank, world_size, all_gather)
+    return sampler
