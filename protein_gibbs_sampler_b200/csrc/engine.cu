@@ -676,7 +676,9 @@ static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int it
       {
         ProfScope ps(e, "msa_col_attention");
         AttnParams ap{e->qkv, e->ctx, e->R, 3 * d, d, d, 2 * d, e->T, 1, e->T, static_cast<long long>(e->R) * e->T};
-        TRY(launch_attention(ap, e->B * e->T, c.heads, hd, st));
+        const char* m = hd == 64 ? launch_msa_col_attention(ap, e->B * e->T, c.heads, st) : "";
+        if (m && *m) return fail("%s", m);
+        if (m) TRY(launch_attention(ap, e->B * e->T, c.heads, hd, st));  // shape not covered: generic kernel
       }
       TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->g_o, e->m_ctx, l.m_cwo, gp(M, d, d, l.c_bo, e->x, d)));
     } else {

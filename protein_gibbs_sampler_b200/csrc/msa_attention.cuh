@@ -179,6 +179,128 @@ __global__ void __launch_bounds__(128) msa_row_pv_kernel(const __half* __restric
   cp_async_wait<0>();
 }
 
+// ---------------------------------------------------------------------------- column attention, R <= 32
+// MSA column attention (fair-esm ColumnSelfAttention): for every alignment column c of MSA b the R rows attend to
+// each other, per head.  The generic flash kernel (attention.cuh) runs it as B*C*H tiny CTAs that each read 128-byte
+// row fragments 4.6 KB apart; here one CTA takes HG adjacent heads of one column, so every row contributes HG*128
+// contiguous bytes of q, of k and of v, and the whole R x R problem of a head sits in two warps' registers (no key
+// loop: R <= 32).  Token r of group s = (b, c) lives in activation row (b*R + r)*C + c.
+template <int HG>
+__global__ void __launch_bounds__(64 * HG) msa_col_attention_kernel(AttnParams p) {
+  constexpr int DH = 64, LDS = DH + 8, KS = DH / 16, NT = DH / 8;
+  extern __shared__ __align__(16) unsigned char col_smem[];
+  __half* sQ = reinterpret_cast<__half*>(col_smem);  // [HG][32 * LDS]
+  __half* sK = sQ + HG * 32 * LDS;
+  __half* sV = sK + HG * 32 * LDS;
+  const int s = blockIdx.x, head0 = blockIdx.y * HG;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+  const long long row0 = (s / p.inner) * p.outer_stride + static_cast<long long>(s % p.inner) * p.inner_stride;
+  const long long rs = static_cast<long long>(p.row_step) * p.ld;
+  const __half* base = p.qkv + row0 * p.ld + head0 * DH;
+  for (int i = tid; i < 32 * HG * 8; i += 64 * HG) {
+    const int r = i / (HG * 8), ch = i % (HG * 8), hl = ch >> 3, c8 = ch & 7;
+    const bool ok = r < p.T;
+    const __half* src = base + static_cast<long long>(ok ? r : 0) * rs + hl * DH + c8 * 8;
+    const int dst = hl * 32 * LDS + r * LDS + c8 * 8;
+    cp_async16(&sQ[dst], src, ok);
+    cp_async16(&sK[dst], src + p.k_off, ok);
+    cp_async16(&sV[dst], src + p.v_off, ok);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+
+  const int hl = warp >> 1, q0 = (warp & 1) * 16;  // this warp: head head0 + hl, query rows q0 .. q0 + 15
+  if (q0 >= p.T) return;
+  const __half* q = sQ + hl * 32 * LDS;
+  const __half* k = sK + hl * 32 * LDS;
+  const __half* v = sV + hl * 32 * LDS;
+  uint32_t qf[KS][4];
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+    ldsm_x4(qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3],
+            &q[(q0 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + ks * 16 + (lane >> 4) * 8]);
+  float sc[4][4];  // 32 keys = 4 n-tiles
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+#pragma unroll
+    for (int kp = 0; kp < KS / 2; ++kp) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4(b0, b1, b2, b3, &k[(j * 8 + (lane & 7)) * LDS + kp * 32 + (lane >> 3) * 8]);
+      mma_16816(sc[j], qf[2 * kp], b0, b1);
+      mma_16816(sc[j], qf[2 * kp + 1], b2, b3);
+    }
+  }
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = j * 8 + 2 * t4;
+    if (c >= p.T) { sc[j][0] = -INFINITY; sc[j][2] = -INFINITY; }
+    if (c + 1 >= p.T) { sc[j][1] = -INFINITY; sc[j][3] = -INFINITY; }
+    mx0 = fmaxf(mx0, fmaxf(sc[j][0], sc[j][1]));
+    mx1 = fmaxf(mx1, fmaxf(sc[j][2], sc[j][3]));
+  }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  constexpr float kLog2e = 1.4426950408889634f;
+  float l0 = 0.f, l1 = 0.f;
+  uint32_t pf[2][4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float p0 = exp2f((sc[j][0] - mx0) * kLog2e), p1 = exp2f((sc[j][1] - mx0) * kLog2e);
+    const float p2 = exp2f((sc[j][2] - mx1) * kLog2e), p3 = exp2f((sc[j][3] - mx1) * kLog2e);
+    l0 += p0 + p1; l1 += p2 + p3;
+    pf[j >> 1][(j & 1) * 2 + 0] = pack2(p0, p1);
+    pf[j >> 1][(j & 1) * 2 + 1] = pack2(p2, p3);
+  }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  float o[NT][4];
+#pragma unroll
+  for (int j = 0; j < NT; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+      uint32_t b0, b1, b2, b3;
+      ldsm_x4_t(b0, b1, b2, b3, &v[(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDS + np * 16 + (lane >> 4) * 8]);
+      mma_16816(o[2 * np], pf[kk], b0, b1);
+      mma_16816(o[2 * np + 1], pf[kk], b2, b3);
+    }
+  }
+  const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+  const int r0 = q0 + g, r1 = r0 + 8;
+  __half* out = p.ctx + row0 * p.ldc + (head0 + hl) * DH;
+  const long long os = static_cast<long long>(p.row_step) * p.ldc;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const int c = j * 8 + 2 * t4;
+    if (r0 < p.T) *reinterpret_cast<uint32_t*>(out + static_cast<long long>(r0) * os + c) = pack2(o[j][0] * i0, o[j][1] * i0);
+    if (r1 < p.T) *reinterpret_cast<uint32_t*>(out + static_cast<long long>(r1) * os + c) = pack2(o[j][2] * i1, o[j][3] * i1);
+  }
+}
+
+// Column attention for head_dim 64, at most 32 rows and a head count divisible by 4 or 2; nullptr on success,
+// "" when the shape is not covered (the caller falls back to the generic kernel), else an error string.
+static const char* launch_msa_col_attention(const AttnParams& p, int groups, int H, cudaStream_t st) {
+  if (p.T > 32) return "";
+  const int hg = H % 4 == 0 ? 4 : (H % 2 == 0 ? 2 : 0);
+  if (!hg) return "";
+  const size_t smem = static_cast<size_t>(3) * hg * 32 * (64 + 8) * sizeof(__half);
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(msa_col_attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4 * 32 * 72 * 2) != cudaSuccess)
+      return "cudaFuncSetAttribute(msa_col_attention_kernel) failed";
+    configured = true;
+  }
+  dim3 grid(groups, H / hg);
+  if (hg == 4) msa_col_attention_kernel<4><<<grid, 256, smem, st>>>(p);
+  else msa_col_attention_kernel<2><<<grid, 128, smem, st>>>(p);
+  if (cudaGetLastError() != cudaSuccess) return "msa_col_attention_kernel launch failed";
+  return nullptr;
+}
+
 // return nullptr on success, else a static error string
 template <int DH>
 static const char* launch_msa_row_attention_t(const __half* qkv, __half* ctx, float* scores, int B, int R, int C,

@@ -133,6 +133,8 @@ def _tokens(cfg, shape, seed):
     ("msa_transformer", 2, 128, 2, 256, (1, 5, 129)),       # ... second tile with a single valid row (L = 128)
     ("msa_transformer", 2, 128, 2, 256, (1, 2, 300)),       # wider than 256 columns: mma.sync row attention
     ("msa_transformer", 2, 128, 4, 256, (1, 3, 70)),        # head_dim 32: mma.sync kernels throughout
+    ("msa_transformer", 2, 128, 2, 256, (1, 40, 12)),       # more than 32 rows: generic column-attention kernel
+    ("msa_transformer", 2, 192, 3, 256, (1, 20, 19)),       # odd head count: generic column-attention kernel
     ("msa_transformer", 12, 768, 12, 3072, (1, 6, 40)),     # full-depth MSA-1b (config 3 model)
 ])
 def test_forward_logits_vs_oracle(arch, layers, d, H, F, shape):
