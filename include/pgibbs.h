@@ -87,6 +87,15 @@ int pgibbs_run_single(pgibbs_engine* e, int32_t first_iter, int32_t num_iters, i
  * Leaves `tokens` resident. */
 int pgibbs_forward_logits(pgibbs_engine* e, const int32_t* tokens, int32_t B, int32_t R, int32_t T,
                           float* logits_out);
+/* Pseudo-log-likelihood pass: replaces the body of log_likelihood_batch (/root/reference/src/pgen/esm_sampler.py:
+ * 316-352, esm_msa_sampler.py:371-424: clone + strided <mask> fill, forward, log_softmax, gather at the true token).
+ * With the UNMASKED tokens and a one-iteration schedule resident (chain c scores positions[c*chain_stride .. +P)),
+ * optionally writes <mask> at the scheduled positions on the device, runs the forward with the LM head on the
+ * scheduled rows only, and returns log_softmax(logits over the whole vocabulary)[targets[slot]] per slot.
+ * targets / logp_out: [n_chains * P]; a target < 0 marks a padding slot (its position must still be valid; result 0).
+ * row >= 0: chains are MSAs and only row `row` of each is masked and scored; row < 0: every sequence is a chain.
+ * The resident tokens are left masked. */
+int pgibbs_score(pgibbs_engine* e, const int32_t* targets, int32_t mask, int32_t row, float* logp_out);
 /* Block until all queued work of this engine has finished; reports asynchronous kernel failures. */
 int pgibbs_sync(pgibbs_engine* e);
 

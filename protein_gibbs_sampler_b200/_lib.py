@@ -38,6 +38,7 @@ SIGNATURES = {
     "pgibbs_run": (c_i32, [c_void_p, c_i32, c_i32, c_i64, c_i32, c_f32, c_i32, c_void_p, c_i32]),
     "pgibbs_run_single": (c_i32, [c_void_p, c_i32, c_i32, c_i64, c_i32, c_f32, c_i32, c_i32, c_void_p, c_i32]),
     "pgibbs_forward_logits": (c_i32, [c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p]),
+    "pgibbs_score": (c_i32, [c_void_p, c_void_p, c_i32, c_i32, c_void_p]),
     "pgibbs_sync": (c_i32, [c_void_p]),
     "pgibbs_debug_read": (c_i32, [c_void_p, c_char_p, c_void_p, c_i64]),
     "pgibbs_debug_layer_limit": (c_i32, [c_void_p, c_i32]),

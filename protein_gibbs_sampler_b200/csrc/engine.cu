@@ -297,6 +297,11 @@ struct pgibbs_engine {
   int64_t rng_chain_offset = 0;  // global index of this engine's first chain (pgibbs_set_chain_offset)
   int32_t* valid_dev = nullptr;
   int32_t* identity_pos = nullptr;  // 0..T-1 (forward_logits)
+  // scoring pass (pgibbs_score): per-slot target ids in, log-probabilities out; live only during that call
+  int32_t* sc_targets = nullptr;
+  float* sc_logp = nullptr;
+  int64_t sc_cap = 0;
+  bool sc_active = false;
   int layer_limit = -1;
   // profiling
   bool prof = false;
@@ -728,6 +733,7 @@ static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int it
     p.seed = e->seed;
     p.rng_row_offset = e->rng_chain_offset * sched.P;
     p.skip_dup_writes = e->has_dup;
+    if (e->sc_active) { p.targets = e->sc_targets; p.logp_out = e->sc_logp; }
     const size_t emb_bytes = static_cast<size_t>(c.vocab) * d * sizeof(float);
     p.emb_in_smem = emb_bytes <= 200 * 1024;
     static bool configured = false;
@@ -844,6 +850,8 @@ int pgibbs_destroy(pgibbs_engine* e) {
   if (e->positions) cudaFree(e->positions);
   if (e->noise) cudaFree(e->noise);
   if (e->valid_dev) cudaFree(e->valid_dev);
+  cudaFree(e->sc_targets);
+  cudaFree(e->sc_logp);
   for (auto& t : e->prof_pending) { cudaEventDestroy(std::get<1>(t)); cudaEventDestroy(std::get<2>(t)); }
   for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -1051,6 +1059,42 @@ int pgibbs_forward_logits(pgibbs_engine* e, const int32_t* tokens, int32_t B, in
   TRY(forward(e, s, e->n_seq, 0, false, 0, -1.f, 0, e->logits));
   CK(cudaMemcpyAsync(logits_out, e->logits, static_cast<size_t>(e->n_seq) * T * e->cfg.vocab * sizeof(float),
                      cudaMemcpyDefault, e->stream));
+  CK(cudaStreamSynchronize(e->stream));
+  TRY(prof_flush(e));
+  return 0;
+}
+
+int pgibbs_score(pgibbs_engine* e, const int32_t* targets, int32_t mask, int32_t row, float* logp_out) {
+  TRY(check_ready(e));
+  if (!e->tokens) return fail("no tokens resident (call pgibbs_set_tokens)");
+  if (!e->positions) return fail("no schedule set (call pgibbs_set_schedule)");
+  if (!targets || !logp_out) return fail("null argument");
+  const bool single = row >= 0;
+  if (single && row >= e->R) return fail("row index out of range");
+  const int n_chains = single ? e->B : e->n_seq;
+  const int64_t rows = static_cast<int64_t>(n_chains) * e->P;
+  if (static_cast<int64_t>(n_chains - 1) * e->chain_stride + e->P > e->positions_used)
+    return fail("schedule buffer too small for %d chains", n_chains);
+  if (rows > e->sc_cap) {
+    cudaFree(e->sc_targets); cudaFree(e->sc_logp);
+    e->sc_targets = nullptr; e->sc_logp = nullptr; e->sc_cap = 0;
+    TRY(dev_alloc(&e->sc_targets, static_cast<size_t>(rows)));
+    TRY(dev_alloc(&e->sc_logp, static_cast<size_t>(rows)));
+    e->sc_cap = rows;
+  }
+  CK(cudaMemcpyAsync(e->sc_targets, targets, rows * sizeof(int32_t), cudaMemcpyDefault, e->stream));
+  Schedule s{e->positions, e->iter_stride, e->chain_stride, e->P, single ? e->R : 1, single ? row : 0};
+  if (mask) {  // the strided <mask> copies are built on the device from the resident (unmasked) tokens
+    ProfScope ps(e, "mask_scatter");
+    mask_scatter_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, e->stream>>>(e->tokens, n_chains, e->T, s,
+                                                                                        0, e->cfg.mask_idx);
+    CK(cudaGetLastError());
+  }
+  e->sc_active = true;
+  const int rc = forward(e, s, n_chains, 0, false, 0, -1.f, 0, nullptr);
+  e->sc_active = false;
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(logp_out, e->sc_logp, rows * sizeof(float), cudaMemcpyDefault, e->stream));
   CK(cudaStreamSynchronize(e->stream));
   TRY(prof_flush(e));
   return 0;

@@ -373,6 +373,9 @@ struct HeadParams {
   int emb_in_smem;
   int no_ln;                 // project g as it is (ESM-1: logits = embed_out . x + bias, no LM-head LayerNorm)
   int skip_dup_writes;       // schedule may contain duplicate positions: last slot wins, like the reference loop
+  // scoring (pseudo-log-likelihood, reference esm_sampler.py:288-363 / esm_msa_sampler.py:319-432)
+  const int32_t* targets;    // [rows] true token of every scheduled slot (< 0: padding slot), or nullptr
+  float* logp_out;           // [rows] log_softmax(logits)[target] over the whole vocabulary
 };
 
 __global__ void __launch_bounds__(256) head_sample_kernel(HeadParams p) {
@@ -445,6 +448,16 @@ __global__ void __launch_bounds__(256) head_sample_kernel(HeadParams p) {
       float* lo = p.logits_out + static_cast<long long>(row) * p.V;
       if (lane < p.V) lo[lane] = mine;
       if (lane + 32 < p.V) lo[lane + 32] = extra;
+    }
+    if (p.logp_out) {
+      const float a = lane < p.V ? mine : -INFINITY, b = lane + 32 < p.V ? extra : -INFINITY;
+      float mx = fmaxf(a, b);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float lse = logf(warp_sum(expf(a - mx) + expf(b - mx))) + mx;
+      const int tgt = __ldg(p.targets + row);
+      const float lt = __shfl_sync(0xffffffffu, tgt >= 32 ? extra : mine, tgt & 31);
+      if (lane == 0) p.logp_out[row] = tgt >= 0 && tgt < p.V ? lt - lse : 0.f;
     }
     if (!p.tokens) continue;
 

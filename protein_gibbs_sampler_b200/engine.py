@@ -143,6 +143,14 @@ class Engine:
         self.shape = (B, R, T)
         return out[:, 0] if squeeze else out
 
+    def score(self, targets, mask=True, row=-1):
+        """log_softmax(logits)[target] for every scheduled slot of the resident tokens (pgibbs_score); targets is
+        [n_chains, P] int, < 0 = padding slot.  Returns float32 of the same shape."""
+        t = torch.as_tensor(targets).to(torch.int32).contiguous()
+        out = torch.empty(t.shape, dtype=torch.float32)
+        check(self.lib.pgibbs_score(self.h, _ptr(t), int(bool(mask)), int(row), _ptr(out)))
+        return out
+
     def sync(self):
         check(self.lib.pgibbs_sync(self.h))
 

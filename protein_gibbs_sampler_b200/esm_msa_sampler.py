@@ -13,7 +13,8 @@ import numpy as np
 import torch
 from tqdm import trange
 
-from .esm_sampler import SchedulePlan, draw_replay_noise, generate_step, in_order_targets, parse_device  # noqa: F401
+from .esm_sampler import (SchedulePlan, draw_replay_noise, generate_step, in_order_targets, parse_device,  # noqa: F401
+                          score_strided)
 
 ESM_MSA_ALLOWED_AMINO_ACIDS = "-ACDEFGHIKLMNPQRSTVWY"
 ESM_MSA_GAP_CHARACTERS = "-"
@@ -306,8 +307,17 @@ class ESM_MSA_sampler():
                     if count_gaps or tok not in gap_tokens:
                         values.append(lp_row[start + pos, tok].item())
 
-            if with_masking:
-                n_copies = int(min(mask_distance, L))
+            n_copies = int(min(mask_distance, L)) if with_masking else 1
+            if hasattr(self.model.model, "require_engine"):
+                # device path: strided <mask> copies built on the GPU, LM head on the masked rows of the target row
+                # only, log_softmax + gather fused into it (Engine.score)
+                per_pos = score_strided(self.model.model.require_engine(), toks, true_toks, start, L, n_copies,
+                                        batch_size or n_copies, with_masking, row=target_index % toks.shape[1])
+                for i in range(n_copies):
+                    for pos in range(i, L, n_copies):
+                        if count_gaps or true_toks[start + pos] not in gap_tokens:
+                            values.append(per_pos[pos])
+            elif with_masking:
                 bs = batch_size or n_copies
                 for b0 in range(0, n_copies, bs):
                     chunk = range(b0, min(b0 + bs, n_copies))

@@ -86,6 +86,16 @@ class SchedulePlan:
         o = it * self.iter_stride + chain * self.chain_stride
         return self.positions[o:o + self.P].tolist()
 
+    def dense(self, n_chains):
+        """Positions as an explicit [n_iters, n_chains, P] array (shared lists broadcast)."""
+        if self.iter_stride == 0:
+            p = self.positions[:self.P].reshape(1, 1, self.P)
+        elif self.chain_stride == 0:
+            p = self.positions.reshape(self.n_iters, 1, self.P)
+        else:
+            p = self.positions.reshape(self.n_iters, n_chains, self.P)
+        return np.broadcast_to(p, (self.n_iters, n_chains, self.P))
+
     def slice_chains(self, lo, hi, n_chains):
         """The plan of chains [lo, hi) out of n_chains (a shared list -- strides 0 -- is everybody's)."""
         if self.chain_stride == 0:
@@ -102,6 +112,44 @@ def draw_replay_noise(n_iters, rows, n_valid, top_k, burnin):
     for it, k in enumerate(ks):
         noise[it, :, :k] = torch.empty(rows, k).exponential_(1)
     return noise, stride
+
+
+def strided_mask_plan(L, n_copies, start):
+    """Positions masked by each strided copy: row i = start + (i, i+n, i+2n, ... < L), padded to P = ceil(L/n) slots
+    by repeating the row's first position.  Returns (positions [n,P] int32, valid [n,P] bool)."""
+    P = -(-L // n_copies)
+    pos = np.empty((n_copies, P), dtype=np.int32)
+    valid = np.zeros((n_copies, P), dtype=bool)
+    for i in range(n_copies):
+        p = np.arange(i, L, n_copies, dtype=np.int32) + start
+        pos[i, :len(p)] = p
+        pos[i, len(p):] = p[0]
+        valid[i, :len(p)] = True
+    return pos, valid
+
+
+def score_strided(engine, unit_tokens, true_row, start, L, n_copies, batch_size, mask, row):
+    """log p(true residue) at each of the L positions of one sequence (row=-1) or of row ``row`` of one MSA, from
+    ``n_copies`` strided-masked copies of ``unit_tokens`` ([1,T] or [1,R,T]) scored ``batch_size`` copies per forward
+    on the device.  Returns a list of L Python floats in position order."""
+    true_row = np.asarray(true_row, dtype=np.int64)
+    if mask:
+        pos, valid = strided_mask_plan(L, n_copies, start)
+    else:   # one unmasked copy, every position scored from it
+        pos, valid = np.arange(start, start + L, dtype=np.int32)[None], np.ones((1, L), dtype=bool)
+        n_copies = 1
+    P = pos.shape[1]
+    targets = np.where(valid, true_row[pos], -1).astype(np.int32)
+    per_pos = np.zeros(L, dtype=np.float32)
+    batch_size = max(1, int(batch_size or n_copies))
+    for b0 in range(0, n_copies, batch_size):
+        b1 = min(b0 + batch_size, n_copies)
+        engine.set_tokens(unit_tokens.repeat(b1 - b0, *([1] * (unit_tokens.dim() - 1))))
+        engine.set_schedule(pos[b0:b1], 1, P, (b1 - b0) * P, P, False)
+        lp = engine.score(targets[b0:b1], mask=mask, row=row).numpy()
+        v = valid[b0:b1]
+        per_pos[pos[b0:b1][v] - start] = lp[v]
+    return [float(x) for x in per_pos]
 
 
 class ESM_sampler():
@@ -224,14 +272,63 @@ class ESM_sampler():
             sequences += self.untokenize_batch(batch, alphabet.prepend_bos, alphabet.append_eos)[0:keep]
         return sequences
 
-    def run_plan(self, tokens, plan, top_k, temperature, burnin, mask):
+    def generate_many(self, seed_seqs, in_order=False, max_len=None, leader_length=0, leader_length_percent=None,
+                      top_k=0, temperature=None, num_iters=10, burnin=float('inf'), mask=True, num_positions=0,
+                      num_positions_percent=None, indexes=None, rollover_from_start=False, max_batch=256):
+        """What ``[self.generate(1, s, batch_size=1, **kw)[0] for s in seed_seqs]`` returns -- the loop of
+        pgen_esm_from_fasta.py:27-33 -- with the independent one-chain calls folded into one device batch per
+        sequence length.  The host RNG draws of every call (position schedule from ``random``,
+        replay noise from torch) are made call by call in that loop's order, and ``seed_seqs`` may be a generator
+        that itself draws from ``random`` (``random.choice(seeds)``) between them, so in replay mode the result is
+        identical to the sequential calls."""
+        calls = []
+        for seed in seed_seqs:
+            if not isinstance(seed, str):
+                raise ValueError("Unknown seed sequence format, expecting str or list")
+            ml = len(seed) if max_len is None else max_len
+            npos = int(ml * (num_positions_percent / 100)) if num_positions_percent is not None else num_positions
+            lead = int(ml * (leader_length_percent / 100)) if leader_length_percent is not None else leader_length
+            tokens = self.get_init_seq(seed, ml, 1)
+            idx, last_i = self.calculate_indexes(indexes, max(lead, 0), ml, rollover_from_start)
+            plan = noise = None
+            if num_iters > 0 and len(idx) > 0:
+                plan, _ = self.plan_positions(1, idx, last_i, min(max(npos, 0), len(idx)), in_order, num_iters)
+                if self.rng == "replay":
+                    noise = draw_replay_noise(plan.n_iters, plan.P, len(self.valid_aa_idx), top_k, burnin)
+            calls.append((tokens, plan, noise))
+        alphabet = self.model.alphabet
+        final = [c[0] for c in calls]
+        groups = {}
+        for i, (tokens, plan, _) in enumerate(calls):
+            if plan is not None:
+                groups.setdefault((tokens.shape[-1], plan.P), []).append(i)
+        for members in groups.values():
+            for m0 in range(0, len(members), max_batch):
+                part = members[m0:m0 + max_batch]
+                plans = [calls[i][1] for i in part]
+                pos = np.concatenate([p.dense(1) for p in plans], axis=1)
+                merged = SchedulePlan(pos, plans[0].n_iters, plans[0].P, len(part) * plans[0].P, plans[0].P,
+                                      any(p.has_duplicates for p in plans))
+                noise = None
+                if self.rng == "replay":
+                    noise = (torch.cat([calls[i][2][0] for i in part], dim=1), calls[part[0]][2][1])
+                out = self.run_plan(torch.cat([calls[i][0] for i in part], dim=0), merged, top_k, temperature, burnin,
+                                    mask, noise=noise)[:, 0]
+                for j, i in enumerate(part):
+                    final[i] = out[j:j + 1]
+        return [self.untokenize_batch(t, alphabet.prepend_bos, alphabet.append_eos)[0] for t in final]
+
+    def run_plan(self, tokens, plan, top_k, temperature, burnin, mask, noise=None):
         """Ship tokens + schedule to the GPU, run every iteration there, return the final tokens [B,R,T].
+        ``noise``: (Exp(1) draws [n_iters, rows, stride], stride) already drawn by the caller (replay mode).
         Raises if the model has no CUDA engine: there is no CPU path."""
         t0 = time.perf_counter()
         engine = self.model.model.require_engine()
         n_chains = int(np.prod(tokens.shape[:-1]))
-        noise = stride = None
-        if self.rng == "replay":   # drawn for ALL chains, in the reference's order, whatever the sharding
+        stride = None
+        if noise is not None:
+            noise, stride = noise
+        elif self.rng == "replay":   # drawn for ALL chains, in the reference's order, whatever the sharding
             noise, stride = draw_replay_noise(plan.n_iters, n_chains * plan.P, len(self.valid_aa_idx), top_k, burnin)
         else:
             device_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
@@ -272,18 +369,26 @@ class ESM_sampler():
 
     def log_likelihood_batch(self, seq_list, with_masking=True, verbose=False, mask_distance=float("inf"),
                              batch_size=None) -> Iterator[Tuple[float, List[float]]]:
-        """Pseudo-log-likelihood with strided masking (reference :288-363).  Every forward here is over
-        equal-length rows, so no <pad> reaches the engine."""
+        """Pseudo-log-likelihood with strided masking (reference :288-363): copy i of the sequence masks positions
+        i, i+n, ... (n = min(mask_distance, L)); each position is scored from the copy that masks it.  With the B200
+        engine the copies are masked on the device, the LM head runs on the masked rows only and the log_softmax +
+        gather at the true residue is fused into it (``Engine.score``): L floats come back instead of n*T*V logits.
+        Any other ``model.model`` (the downward duck-typed interface) is called for logits as the reference does.
+        Every forward here is over equal-length rows, so no <pad> reaches the engine."""
         alphabet = self.model.alphabet
         if batch_size is None:
             batch_size = len(seq_list)
         start = 1 if alphabet.prepend_bos else 0
+        on_engine = hasattr(self.model.model, "require_engine")
         for seq in seq_list:
             cleaned = self.clean_seed_seq(seq)
             L = len(cleaned)
             true_toks = self.model.batch_converter([("0", cleaned)])[2][0]
-            if with_masking:
-                n_copies = int(min(mask_distance, L))
+            n_copies = int(min(mask_distance, L)) if with_masking else 1
+            if on_engine:
+                per_pos = score_strided(self.model.model.require_engine(), true_toks[None], true_toks, start, L,
+                                        n_copies, batch_size, with_masking, row=-1)
+            elif with_masking:
                 toks = true_toks.repeat(n_copies, 1)
                 for i in range(n_copies):
                     toks[i, start + i:start + L:n_copies] = alphabet.mask_idx
@@ -294,11 +399,11 @@ class ESM_sampler():
                         i = b0 + j
                         for pos in range(i, L, n_copies):
                             per_pos[pos] = lp[j, start + pos, true_toks[start + pos]].item()
-                # the reference accumulates copy by copy; keep its output ordering
-                ordered = [per_pos[pos] for i in range(n_copies) for pos in range(i, L, n_copies)]
             else:
                 lp = torch.log_softmax(self.model.model(true_toks[None])["logits"], dim=-1)[0]
-                ordered = [lp[start + pos, true_toks[start + pos]].item() for pos in range(L)]
+                per_pos = [lp[start + pos, true_toks[start + pos]].item() for pos in range(L)]
+            # the reference accumulates copy by copy; keep its output ordering
+            ordered = [per_pos[pos] for i in range(n_copies) for pos in range(i, L, n_copies)]
             total = np.float32(0.0)   # the reference sums 0-d float32 tensors
             for v in ordered:
                 total = np.float32(total + np.float32(v))

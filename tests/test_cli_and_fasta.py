@@ -128,7 +128,11 @@ def _flags(parser):
 
 
 @pytest.mark.parametrize("module,ref_file", [("pgen_esm", "pgen_esm.py"), ("pgen_msa", "pgen_msa.py"),
-                                             ("pgen_msa_revised", "pgen_msa_revised.py")])
+                                             ("pgen_msa_revised", "pgen_msa_revised.py"),
+                                             ("pgen_esm_from_fasta", "pgen_esm_from_fasta.py"),
+                                             ("likelihood_esm", "likelihood_esm.py"),
+                                             ("likelihood_esm_msa", "likelihood_esm_msa.py"),
+                                             ("clean_fasta", "clean_fasta.py")])
 def test_cli_flags_match_reference(module, ref_file):
     """Every flag of the reference script exists here with the same default and action; only --device defaults to
     the GPU (the engine has no CPU path) and --model lists the models this engine implements."""
@@ -138,7 +142,8 @@ def test_cli_flags_match_reference(module, ref_file):
     path = os.path.join(REF, ref_file)
     if not os.path.exists(path):
         pytest.skip("reference source not present on this machine")
-    src = open(path).read()
+    src = "".join(ln for ln in open(path) if not ln.lstrip().startswith("#"))   # commented-out flags do not exist
+    src = re.sub(r"add_argument\(\s*'(-{1,2}[A-Za-z_]+)'", r'add_argument("\1"', src)   # either quote style
     ref_flags = re.findall(r'add_argument\(\s*"(-{1,2}[A-Za-z_]+)"', src)
     assert ref_flags and set(ref_flags) == set(ours), (sorted(ref_flags), sorted(ours))
     for flag in ref_flags:
@@ -151,11 +156,150 @@ def test_cli_flags_match_reference(module, ref_file):
         want = eval(m.group(1), {"sys": sys})
         assert default == want, (flag, default, want)
         assert ("store_true" in call) == (action == "_StoreTrueAction"), flag
-    assert ours["--device"][0] == "gpu"
+    assert "--device" not in ours or ours["--device"][0] == "gpu"
+
+
+def test_clean_fasta_cli(tmp_path):
+    from protein_gibbs_sampler_b200.cli import clean_fasta
+    (tmp_path / "in.a2m").write_text(A2M)
+    for mode, want in (("delete", CORE), ("unalign", FULL)):
+        clean_fasta.cli(["-i", str(tmp_path / "in.a2m"), "-o", str(tmp_path / "out.fa"), "--clean_strategy", mode])
+        names, seqs = fasta.parse_fasta(tmp_path / "out.fa", return_names=True)
+        assert names == ["seq_1", "seq_2", "seq_3"] and seqs[0] == want and seqs[2] == want
+    clean_fasta.cli(["-i", str(tmp_path / "in.a2m"), "-o", str(tmp_path / "out.fa"), "--clean_strategy", "upper",
+                     "--full_name"])
+    assert fasta.parse_fasta(tmp_path / "out.fa", return_names=True, full_name=True)[0][1] == \
+        "seq_2 second record has a description"
+
+
+def _loglik_golden():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_loglik.json")) as f:
+        return json.load(f)
+
+
+def test_likelihood_esm_cli_table_vs_reference_values(tmp_path):
+    """Host logic of the likelihood_esm drop-in: FASTA in (gaps / stop codons stripped), `id <sep> score` table and the
+    ';'-joined position-wise file out; the numbers are the reference sampler's own (golden, fp32 oracle model)."""
+    from oracle.fair_esm import OracleModel
+    from protein_gibbs_sampler_b200.cli import likelihood_esm
+    from protein_gibbs_sampler_b200.esm_sampler import ESM_sampler
+    from protein_gibbs_sampler_b200.weights import synthetic_state_dict
+    c = [c for c in _loglik_golden()["esm"] if len(c["seqs"]) == 2 and c["kwargs"].get("mask_distance") == 4][0]
+    s = ESM_sampler(OracleModel(c["cfg"], synthetic_state_dict(c["cfg"], c["weights_seed"])), device="cpu")
+    text = ">first some description\n%s-*\n>second\n%s\n" % (c["seqs"][0][:4] + "-" + c["seqs"][0][4:].lower(), c["seqs"][1])
+    for csv, sep in ((False, "\t"), (True, ",")):
+        out, pos = io.StringIO(), tmp_path / "pos.txt"
+        likelihood_esm.main(io.StringIO(text), out, False, s, 2, 4, csv, "myscore", str(pos), show_progress_bar=False)
+        lines = out.getvalue().strip().split("\n")
+        assert lines[0] == "id%smyscore" % sep and [ln.split(sep)[0] for ln in lines[1:]] == ["first", "second"]
+        for ln, (mean, each) in zip(lines[1:], c["result"]):
+            assert float(ln.split(sep)[1]) == pytest.approx(mean, abs=2e-6)
+        plines = pos.read_text().strip().split("\n")
+        assert plines[0] == "id%smyscore" % sep
+        for ln, (mean, each) in zip(plines[1:], c["result"]):
+            assert [float(v) for v in ln.split(sep)[1].split(";")] == pytest.approx([round(v, 3) for v in each], abs=1.1e-3)
+    args = likelihood_esm.build_parser().parse_args(["--masking_off", "--mask_distance", "3"])
+    with pytest.raises(ValueError, match="both set"):
+        likelihood_esm.mask_distance_arg(args)
+    with pytest.raises(ValueError, match=">= 1"):
+        likelihood_esm.mask_distance_arg(likelihood_esm.build_parser().parse_args(["--mask_distance", "0"]))
+
+
+def test_likelihood_esm_msa_cli_contexts(tmp_path):
+    """likelihood_esm_msa drop-in, host logic: the query goes on top of the (subset of the) reference alignment,
+    columns where the query has a gap are deleted, the top row is scored; `in_msas` bypasses the reference MSA."""
+    from oracle.fair_esm import OracleModel
+    from protein_gibbs_sampler_b200.cli import likelihood_esm_msa as cli
+    from protein_gibbs_sampler_b200.esm_msa_sampler import ESM_MSA_sampler
+    from protein_gibbs_sampler_b200.weights import synthetic_state_dict
+    c = _loglik_golden()["msa"][0]
+    s = ESM_MSA_sampler(OracleModel(c["cfg"], synthetic_state_dict(c["cfg"], c["weights_seed"])), device="cpu")
+    ref = ["MKTAYIAK-RQ", "MKTAYLAKQRQ", "MRTAY-AKQRQ"]
+    queries = {"q1": "MK-AYIAKQRQ", "q2": "MKTAWIAKQR-"}
+    qtext = "".join(">%s\n%s\n" % kv for kv in queries.items())
+    rtext = "".join(">r%d\n%s\n" % (i, r) for i, r in enumerate(ref))
+    out = io.StringIO()
+    cli.main(io.StringIO(qtext), out, False, s, io.StringIO(rtext), subset_strategy="in_order", alignment_size=2,
+             mask_distance=3, positionwise=str(tmp_path / "p.tsv"), show_progress_bar=False)
+    lines = out.getvalue().strip().split("\n")
+    assert lines[0] == "id\tesm-msa" and [ln.split("\t")[0] for ln in lines[1:]] == ["q1", "q2"]
+    for ln, (name, q) in zip(lines[1:], queries.items()):
+        gaps = [i for i, ch in enumerate(q) if ch == "-"]
+        msa = cli.delete_msa_cols([q] + ref[:2], gaps)
+        assert all(len(r) == 10 for r in msa) and "-" not in msa[0]
+        want, each = s.log_likelihood(msa, mask_distance=3)
+        assert float(ln.split("\t")[1]) == pytest.approx(want, abs=1e-6) and len(each) == 10
+    assert len((tmp_path / "p.tsv").read_text().strip().split("\n")[1].split("\t")[1].split(";")) == 10
+    # user-supplied alignments: the golden MSA itself, query row first
+    out = io.StringIO()
+    cli.main(io.StringIO(">x\n%s\n" % c["msas"][0][0]), out, False, s, in_msas={"x": c["msas"][0]}, csv=True,
+             show_progress_bar=False)
+    gaps = [i for i, ch in enumerate(c["msas"][0][0]) if ch == "-"]
+    want = s.log_likelihood(cli.delete_msa_cols(c["msas"][0], gaps))[0]
+    assert float(out.getvalue().strip().split("\n")[1].split(",")[1]) == pytest.approx(want, abs=1e-6)
+    # redraw advances the subset seed by 1e6 per query (reference :98-101)
+    b = cli.ContextBuilder(queries, None, ref, "random", 2, subset_random_seed=5, redraw=True)
+    b("q1"); b("q2")
+    assert b.seed == 2000005
 
 
 # ------------------------------------------------------------------------------------------------ GPU: end to end
 AA = set("ACDEFGHIKLMNPQRSTVWY")
+
+
+@pytest.mark.gpu
+def test_likelihood_cli_on_engine(tmp_path, gpu_lib):
+    """Both likelihood drop-ins end to end on the engine (synthetic weights): tables well-formed, values equal to
+    the sampler API's."""
+    from protein_gibbs_sampler_b200.cli import likelihood_esm, likelihood_esm_msa
+    seqs = {"a": "MKTAYIAKQRQISFVKSHFSRQLEE", "b": "MKTAYIAKQR"}
+    (tmp_path / "in.fa").write_text("".join(">%s\n%s\n" % kv for kv in seqs.items()))
+    likelihood_esm.cli(["-i", str(tmp_path / "in.fa"), "-o", str(tmp_path / "out.tsv"), "--model", "esm2_t6_8M",
+                        "--device", "cuda:0", "--mask_distance", "5", "--batch_size", "2",
+                        "--positionwise", str(tmp_path / "pos.tsv")])
+    rows = [ln.split("\t") for ln in (tmp_path / "out.tsv").read_text().strip().split("\n")]
+    assert rows[0] == ["id", "esm2_t6_8M"] and [r[0] for r in rows[1:]] == ["a", "b"]
+    assert all(-8.0 < float(r[1]) < 0.0 for r in rows[1:])
+    pos = [ln.split("\t") for ln in (tmp_path / "pos.tsv").read_text().strip().split("\n")][1:]
+    assert [len(p[1].split(";")) for p in pos] == [25, 10]
+    (tmp_path / "ref.fa").write_text(">r0\nMKTAYLAKQR\n>r1\nMRTAY-AKQR\n>r2\nMKTAWIAKQR\n")
+    (tmp_path / "q.fa").write_text(">q\nMKTAYIAK-R\n")
+    likelihood_esm_msa.cli(["-i", str(tmp_path / "q.fa"), "-o", str(tmp_path / "m.csv"), "--csv", "--reference_msa",
+                            str(tmp_path / "ref.fa"), "--subset_strategy", "in_order", "--device", "gpu"])
+    rows = [ln.split(",") for ln in (tmp_path / "m.csv").read_text().strip().split("\n")]
+    assert rows[0] == ["id", "esm-msa"] and rows[1][0] == "q" and -8.0 < float(rows[1][1]) < 0.0
+
+
+@pytest.mark.gpu
+def test_pgen_esm_from_fasta_cli_and_generate_many(tmp_path, gpu_lib):
+    """pgen_esm_from_fasta drop-in.  generate_many folds the reference's one-chain-per-output loop
+    (pgen_esm_from_fasta.py:27-33) into one device batch per seed length; in replay mode the output is identical to
+    that loop run call by call with the same seeds of `random` / torch."""
+    import random
+    import torch
+    from protein_gibbs_sampler_b200 import models
+    from protein_gibbs_sampler_b200.cli import pgen_esm_from_fasta as cli
+    from protein_gibbs_sampler_b200.esm_sampler import ESM_sampler
+    seeds = ["MKTAYIAKQR-ISFVK", "MKT.AYLAKQRQISFVKSH", "mrtayiakqrq-sfvk"]
+    (tmp_path / "seeds.fa").write_text("".join(">s%d\n%s\n" % (i, q) for i, q in enumerate(seeds)))
+    kw = dict(num_iters=3, burnin=1, top_k=2, num_positions_percent=30, leader_length=2)
+    s = ESM_sampler(models.ESM2_t6_8M(seed=1), device="cuda:0", rng="replay")
+    random.seed(3); torch.manual_seed(3)
+    folded = cli.sample_from_seeds(s, seeds, 7, kw, keep_gap_positions=True)
+    random.seed(3); torch.manual_seed(3)
+    looped = []
+    for _ in range(7):
+        seed, gap_mask = fasta.unalign(random.choice(seeds))
+        looped.append(fasta.add_gaps_back(s.generate(1, seed, batch_size=1, show_progress_bar=False, **kw)[0], gap_mask))
+    assert folded == looped
+    assert {len(q) for q in folded} <= {len(q) for q in seeds}
+    spec = tmp_path / "spec.tsv"
+    spec.write_text("fam\t%r\t%s\nignored line\n" % (kw, tmp_path / "seeds.fa"))
+    cli.cli(["-i", str(spec), "-o", str(tmp_path / "out"), "--num_output_sequences", "5", "--device", "cuda:0",
+             "--model", "esm2_t6_8M"])
+    names, seqs = fasta.parse_fasta(tmp_path / "out" / "fam.fasta", return_names=True)
+    assert names == [str(i) for i in range(5)] and all(set(q) <= AA and len(q) in (15, 18) for q in seqs)
 
 
 @pytest.mark.gpu

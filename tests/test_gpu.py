@@ -302,3 +302,54 @@ def test_esm1_generate_matches_oracle_loop():
     assert len(got) == 3 and all(len(x) == 22 and set(x) <= set("ACDEFGHIKLMNPQRSTVWY") for x in got)
     diff = sum(a != b for x, y in zip(got, want) for a, b in zip(x, y))
     assert diff <= 2, (got, want)
+
+
+# ------------------------------------------------------------------------------------------------ scoring
+@pytest.mark.parametrize("arch,H,length,rows,mask_distance,batch_size", [
+    ("roberta_large", 2, 23, 1, float("inf"), None), ("roberta_large", 2, 23, 1, 5, 2), ("esm2", 2, 131, 1, 7, 3),
+    ("esm1", 2, 30, 1, 4, None), ("roberta_large", 2, 20, 1, None, None),
+    ("msa_transformer", 2, 19, 4, 6, 4), ("msa_transformer", 2, 19, 3, float("inf"), 5), ("msa_transformer", 2, 19, 3, None, 1),
+])
+def test_device_scoring_equals_logits_path(arch, H, length, rows, mask_distance, batch_size):
+    """Engine.score (on-device strided <mask>, LM head on the masked rows, fused log_softmax + gather) against the
+    same quantity computed on the host from forward_logits of host-masked copies, as the reference's
+    log_likelihood_batch does it (esm_sampler.py:316-352, esm_msa_sampler.py:371-424).  Same forward, so only the
+    fp32 log_softmax differs: 2e-5 absolute.  mask_distance None = --masking_off."""
+    from protein_gibbs_sampler_b200.config import tiny_config
+    from protein_gibbs_sampler_b200.esm_sampler import ESM_ALLOWED_AMINO_ACIDS
+    cfg = tiny_config(arch, 2, 128, H, 256)
+    s, _ = make(cfg, 11)
+    rnd = random.Random(length * 7 + rows)
+    seqs = ["".join(rnd.choice(ESM_ALLOWED_AMINO_ACIDS) for _ in range(length)) for _ in range(rows)]
+    masking = mask_distance is not None
+    md = mask_distance if masking else float("inf")
+    alphabet = s.model.alphabet
+    start = 1 if alphabet.prepend_bos else 0
+    engine = s.model.model.require_engine()
+    if arch == "msa_transformer":
+        seqs[1] = "-" + seqs[1][1:5] + "--" + seqs[1][7:]          # gaps in the target row are skipped
+        target = 1
+        mean, each = s.log_likelihood(seqs, target_index=target, with_masking=masking, mask_distance=md)
+        toks = s.model.batch_converter([[(str(i), q) for i, q in enumerate(seqs)]])[2]
+        true = toks[0, target]
+        scored = [i for i in range(length) if seqs[target][i] != "-"]
+    else:
+        mean, each = next(s.log_likelihood_batch(seqs[:1], with_masking=masking, mask_distance=md, batch_size=batch_size))
+        toks = s.model.batch_converter([("0", seqs[0])])[2]
+        true = toks[0]
+        scored = list(range(length))
+    n = int(min(md, length)) if masking else 1
+    want = {}
+    for i in range(n):
+        t = toks.clone()
+        row = t[0, target] if arch == "msa_transformer" else t[0]
+        if masking:
+            row[start + i:start + length:n] = alphabet.mask_idx
+        lp = torch.log_softmax(engine.forward_logits(t), dim=-1)[0]
+        lp = lp[target] if arch == "msa_transformer" else lp
+        for pos in range(i, length, n):
+            want[pos] = lp[start + pos, true[start + pos]].item()
+    order = [pos for i in range(n) for pos in range(i, length, n) if pos in scored]
+    assert len(each) == len(order)
+    assert each == pytest.approx([want[pos] for pos in order], abs=2e-5)
+    assert mean == pytest.approx(sum(want[pos] for pos in order) / len(order), abs=2e-5)

@@ -226,3 +226,17 @@ def test_esm1_alphabet_ids_pinned_by_reference_fixtures():
     toks = a.get_batch_converter()([("0", "AA<mask>")])[2]
     assert toks.tolist() == [[32, 5, 5, 33]]
     assert sorted(a.get_idx(t) for t in "ACDEFGHIKLMNPQRSTVWY") == list(range(4, 24))
+
+
+def test_strided_mask_plan_covers_every_position_once():
+    """Scoring schedule (log_likelihood_batch's `toks[i, start+i : start+L : n] = mask`, reference
+    esm_sampler.py:323-326): copy i masks i, i+n, ...; padded slots repeat the copy's first position."""
+    import numpy as np
+    from protein_gibbs_sampler_b200.esm_sampler import strided_mask_plan
+    for L, n, start in [(10, 10, 1), (10, 3, 1), (7, 1, 0), (257, 16, 1), (5, 4, 1)]:
+        pos, valid = strided_mask_plan(L, n, start)
+        assert pos.shape == valid.shape == (n, -(-L // n))
+        assert sorted(pos[valid].tolist()) == list(range(start, start + L))
+        for i in range(n):
+            assert pos[i][valid[i]].tolist() == list(range(start + i, start + L, n))
+            assert (pos[i][~valid[i]] == start + i).all()
