@@ -117,6 +117,9 @@ static int g_num_sms = 0;
 
 // A GEMM's tiling: tile width and whether a CTA pair (cta_group::2, 256-row tiles) computes it.
 // The B tensor map's box holds bn / cg rows.
+constexpr int kSplitFlagInts = 4096;  // K-split flags: >= 148 groups x 2 ranks x 8 epilogue warps
+static int g_gemm_split = 1;          // PGIBBS_GEMM_SPLIT=0 turns the last-wave K-split off (A/B measurements)
+
 struct GemmPlan {
   int bn = 256, cg = 2;
   int b_box() const { return bn / cg; }
@@ -136,6 +139,14 @@ static int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const Ge
   }
   const int m_tiles = (p.M + kBM * CG - 1) / (kBM * CG), n_tiles = (p.N + BN - 1) / BN;
   const int groups = std::min(g_num_sms / CG, m_tiles * n_tiles);
+  GemmParams q = p;
+  q.split = 1;
+  if (EPI == EPI_RESID_F32 && p.flags && g_gemm_split) {
+    // partly-filled last wave: cut its tiles along K so that the idle groups take a share (gemm_work_unit)
+    const int tiles = m_tiles * n_tiles, rem = tiles % groups;
+    if (tiles > groups && rem) q.split = std::min({groups / rem, 4, p.K / kBK / 4, kSplitFlagInts / (rem * CG * kEpiWarps)});
+    if (q.split < 2) q.split = 1;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(groups * CG);
   cfg.blockDim = dim3(kGemmThreads);
@@ -146,7 +157,7 @@ static int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const Ge
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  CK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG>, a, b, c, p));
+  CK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG>, a, b, c, q));
   return 0;
 }
 
@@ -297,6 +308,9 @@ struct pgibbs_engine {
   int64_t rng_chain_offset = 0;  // global index of this engine's first chain (pgibbs_set_chain_offset)
   int32_t* valid_dev = nullptr;
   int32_t* identity_pos = nullptr;  // 0..T-1 (forward_logits)
+  // last-wave K-split of the residual GEMMs (gemm.cuh: gemm_work_unit): ordering flags, launch counter
+  int32_t* split_flags = nullptr;
+  int split_epoch = 0;
   // scoring pass (pgibbs_score): per-slot target ids in, log-probabilities out; live only during that call
   int32_t* sc_targets = nullptr;
   float* sc_logp = nullptr;
@@ -521,6 +535,7 @@ static int run_gather_f32(pgibbs_engine* e, const float* x, float* out, int rows
 
 static int run_gemm(pgibbs_engine* e, const char* name, int epi, GemmPlan g, const CUtensorMap& a,
                     const CUtensorMap& b, GemmParams p) {
+  if (epi == EPI_RESID_F32) { p.flags = e->split_flags; p.epoch = ++e->split_epoch; }
   ProfScope ps(e, name);
   return launch_gemm(epi, g, a, b, p, e->stream);
 }
@@ -819,6 +834,7 @@ int pgibbs_create(const pgibbs_model_config* cfg, int32_t device_id, pgibbs_engi
   if (prop.major != 10) return fail("device %d is sm_%d%d; this engine only runs on sm_100 (B200)", device_id, prop.major, prop.minor);
   g_num_sms = prop.multiProcessorCount;
   if (const char* f = getenv("PGIBBS_GEMM_CG")) g_force_cg = atoi(f);
+  if (const char* f = getenv("PGIBBS_GEMM_SPLIT")) g_gemm_split = atoi(f);
   if (cfg->embed_dim % cfg->heads) return fail("embed_dim %% heads != 0");
   if (cfg->embed_dim % 64 || cfg->ffn_dim % 64) return fail("embed_dim and ffn_dim must be multiples of 64");
   if (cfg->embed_dim > kMaxVecPerLane * 128) return fail("embed_dim %d too large (max %d)", cfg->embed_dim, kMaxVecPerLane * 128);
@@ -835,6 +851,11 @@ int pgibbs_create(const pgibbs_model_config* cfg, int32_t device_id, pgibbs_engi
     return fail("cudaStreamCreate failed");
   }
   e->stream = e->own_stream;
+  if (cudaMalloc(&e->split_flags, kSplitFlagInts * sizeof(int32_t)) != cudaSuccess ||
+      cudaMemset(e->split_flags, 0, kSplitFlagInts * sizeof(int32_t)) != cudaSuccess) {
+    pgibbs_destroy(e);
+    return fail("cudaMalloc of the GEMM split flags failed");
+  }
   *out = e;
   return 0;
 }
@@ -852,6 +873,7 @@ int pgibbs_destroy(pgibbs_engine* e) {
   if (e->valid_dev) cudaFree(e->valid_dev);
   cudaFree(e->sc_targets);
   cudaFree(e->sc_logp);
+  cudaFree(e->split_flags);
   for (auto& t : e->prof_pending) { cudaEventDestroy(std::get<1>(t)); cudaEventDestroy(std::get<2>(t)); }
   for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -1206,10 +1228,15 @@ int pgibbs_op_gemm(int32_t device_id, const float* A, const float* B, const floa
   const size_t na = static_cast<size_t>(M) * K, nb = static_cast<size_t>(N) * K, nc = static_cast<size_t>(M) * N;
   float *dA = nullptr, *dB = nullptr, *dbias = nullptr, *dC32 = nullptr;
   __half *hA = nullptr, *hB = nullptr, *dC16 = nullptr;
+  int32_t* dflags = nullptr;
+  int epoch = 0;
   int rc = 0;
   cudaStream_t st = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (const char* f = getenv("PGIBBS_GEMM_SPLIT")) g_gemm_split = atoi(f);
   auto body = [&]() -> int {
+    TRY(dev_alloc(&dflags, static_cast<size_t>(kSplitFlagInts)));
+    CK(cudaMemset(dflags, 0, kSplitFlagInts * sizeof(int32_t)));
     TRY(dev_alloc(&dA, na)); TRY(dev_alloc(&dB, nb)); TRY(dev_alloc(&hA, na)); TRY(dev_alloc(&hB, nb));
     TRY(dev_alloc(&dC32, nc)); TRY(dev_alloc(&dC16, nc));
     CK(cudaMemcpy(dA, A, na * sizeof(float), cudaMemcpyDefault));
@@ -1226,7 +1253,8 @@ int pgibbs_op_gemm(int32_t device_id, const float* A, const float* B, const floa
     TRY(make_tmap_2d(&ma, hA, M, K, K, kBM));
     TRY(make_tmap_2d(&mb, hB, N, K, K, plan.b_box()));
     GemmParams p = gp(M, N, K, dbias, out16 ? static_cast<void*>(dC16) : static_cast<void*>(dC32), N);
-    auto launch_plan = [&]() -> int { return launch_gemm(epilogue, plan, ma, mb, p, st); };
+    p.flags = dflags;
+    auto launch_plan = [&]() -> int { p.epoch = ++epoch; return launch_gemm(epilogue, plan, ma, mb, p, st); };
     TRY(launch_plan());
     CK(cudaStreamSynchronize(st));
     if (out16) {
@@ -1250,7 +1278,7 @@ int pgibbs_op_gemm(int32_t device_id, const float* A, const float* B, const floa
   };
   rc = body();
   for (void* p : {static_cast<void*>(dA), static_cast<void*>(dB), static_cast<void*>(dbias), static_cast<void*>(dC32),
-                  static_cast<void*>(hA), static_cast<void*>(hB), static_cast<void*>(dC16)})
+                  static_cast<void*>(hA), static_cast<void*>(hB), static_cast<void*>(dC16), static_cast<void*>(dflags)})
     if (p) cudaFree(p);
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);

@@ -42,6 +42,10 @@ struct GemmParams {
   int head_dim;
   int seq_len;          // token position t = row % seq_len
   const float2* rope;   // [seq_len, head_dim/2] (cos, sin)
+  // EPI_RESID_F32 only: K-split of the partly-filled last wave (see gemm_work_unit).  split <= 1: off.
+  int split;            // parts each last-wave tile is cut into along K
+  int epoch;            // launch counter of the owner of `flags` (strictly increasing)
+  int32_t* flags;       // [last-wave tile][part][CTA rank][epilogue warp] = epoch once that warp's reduce-adds landed
 };
 
 constexpr int kBM = 128;
@@ -103,6 +107,45 @@ __device__ __forceinline__ void rope_chunk(float (&v)[64], const float2* __restr
   }
 }
 
+// Static schedule of one CTA group (a CTA, or a CTA pair): tiles group, group + G, group + 2G, ...  When the tile count
+// is not a multiple of G the last wave leaves G - rem groups idle for a whole tile time (out-projection / FC2 at
+// config 2: 325 tiles on 74 pairs = 4.39 waves run as 5).  For the residual epilogue -- whose output is ADDED to the
+// fp32 stream, so partial sums over K can be added one after the other -- each last-wave tile is cut into `split`
+// parts along K, run by `split` different groups at the same time.  The parts' reduce-adds are ordered (part j's
+// epilogue warp waits for a flag from the same warp of part j-1, which owns the same output chunks), so every
+// element is still x + p0 + p1 + ... in one fixed order: the result does not depend on timing.
+struct WorkUnit {
+  int tile, kb0, kb1;
+  int part;   // -1: whole tile; otherwise which K part
+  int slot;   // index of the tile inside the last wave (flag addressing)
+};
+__device__ __forceinline__ bool gemm_work_unit(int it, int group, int num_groups, int num_tiles, int num_kb, int split,
+                                               WorkUnit& u) {
+  u.part = -1; u.slot = 0; u.kb0 = 0; u.kb1 = num_kb;
+  u.tile = group + it * num_groups;
+  if (split <= 1) return u.tile < num_tiles;
+  const int full_waves = num_tiles / num_groups;
+  if (it < full_waves) return true;
+  if (it > full_waves) return false;
+  const int rem = num_tiles - full_waves * num_groups;
+  if (group >= rem * split) return false;
+  u.slot = group / split;
+  u.part = group - u.slot * split;
+  u.tile = full_waves * num_groups + u.slot;
+  u.kb0 = u.part * num_kb / split;
+  u.kb1 = (u.part + 1) * num_kb / split;
+  return true;
+}
+
+__device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int32_t* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // Drain one accumulator tile row-slice.  This warp owns TMEM lanes [quad*32, quad*32+32) (= 32 output rows, one per
 // thread) and every second chunk (`par`) of 128 output bytes per row (64 fp16 / 32 fp32 columns).  Each chunk is
 // staged in this warp's own 128B-swizzled shared-memory buffer and written by one TMA store (or TMA reduce-add
@@ -110,7 +153,8 @@ __device__ __forceinline__ void rope_chunk(float (&v)[64], const float2* __restr
 //   t_row = TMEM address of the slice's column 0; row0 = first output row of the slice; n0 = first output column.
 template <int BN, int EPI>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CUtensorMap* tmC, uint32_t t_row,
-                                                   int row0, int lane, int n0, int par, uint8_t* staging, int& sbuf) {
+                                                   int row0, int lane, int n0, int par, uint8_t* staging, int& sbuf,
+                                                   bool add_bias = true) {
   constexpr bool kOut16 = epi_out_f16(EPI);
   constexpr int kCW = kOut16 ? 64 : 32;  // columns per chunk
   static_assert(BN % kCW == 0, "tile width must be a whole number of epilogue chunks");
@@ -127,7 +171,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[hlf * 32 + j] = __uint_as_float(r[j]);
     }
-    if (p.bias) {
+    if (p.bias && add_bias) {
       if (g + kCW <= p.N) {
 #pragma unroll
         for (int j4 = 0; j4 < kCW / 4; ++j4) {
@@ -217,6 +261,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
   const int num_kb = p.K / kBK;
+  const int split = EPI == EPI_RESID_F32 ? p.split : 1;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -252,10 +297,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool issuer = elect_one();
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = group; tile < num_tiles; tile += num_groups) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+    WorkUnit u;
+    for (int it = 0; gemm_work_unit(it, group, num_groups, num_tiles, num_kb, split, u); ++it) {
+      const int m_blk = u.tile / n_tiles, n_blk = u.tile % n_tiles;
       const int a_row = (m_blk * CG + rank) * kBM, b_row = n_blk * BN + rank * kBNL;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = u.kb0; kb < u.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = ring + stage * kStageBytes;
         if (issuer) {
@@ -282,11 +328,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       int as = 0;
       uint32_t aphase = 0;
       const uint32_t desc_hi = static_cast<uint32_t>(make_smem_desc_sw128(0, 1024) >> 32);
-      for (int tile = group; tile < num_tiles; tile += num_groups) {
+      WorkUnit u;
+      for (int it = 0; gemm_work_unit(it, group, num_groups, num_tiles, num_kb, split, u); ++it) {
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + as * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = u.kb0; kb < u.kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(ring + stage * kStageBytes);
@@ -298,8 +345,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               // +32 bytes per UMMA_K slice inside the 128B swizzle row (address field is >>4)
               const uint64_t adesc = (static_cast<uint64_t>(desc_hi) << 32) | (a_lo + 2 * k);
               const uint64_t bdesc = (static_cast<uint64_t>(desc_hi) << 32) | (b_lo + 2 * k);
-              if constexpr (CG == 2) umma_f16_ss_pair(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
-              else umma_f16_ss(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0 ? 1u : 0u);
+              const uint32_t acc = (kb != u.kb0 || k != 0) ? 1u : 0u;
+              if constexpr (CG == 2) umma_f16_ss_pair(d_tmem, adesc, bdesc, kIdesc, acc);
+              else umma_f16_ss(d_tmem, adesc, bdesc, kIdesc, acc);
             }
             // frees this smem stage (in both CTAs) when the MMAs above retire
             if constexpr (CG == 2) umma_commit_pair(&empty_bar[stage], 0b11); else umma_commit(&empty_bar[stage]);
@@ -325,13 +373,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t leader_empty = CG == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0;
     uint8_t* my_staging = staging + ew * 2 * kEpiStageBytes;
     int sbuf = 0;
-    for (int tile = group; tile < num_tiles; tile += num_groups) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+    WorkUnit u;
+    for (int it = 0; gemm_work_unit(it, group, num_groups, num_tiles, num_kb, split, u); ++it) {
+      const int m_blk = u.tile / n_tiles, n_blk = u.tile % n_tiles;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const int row0 = (m_blk * CG + rank) * kBM + quad * 32;
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + as * BN;
-      gemm_epilogue_tile<BN, EPI>(p, &tmC, t_row, row0, lane, n_blk * BN, par, my_staging, sbuf);
+      if constexpr (EPI == EPI_RESID_F32) {
+        // K-split tile: this warp's chunks are added after the same warp of the previous part has added its own
+        int32_t* flag = p.flags + ((u.slot * split + (u.part > 0 ? u.part : 0)) * CG + rank) * kEpiWarps + ew;
+        if (u.part > 0) {
+          if (lane == 0) while (ld_acquire_gpu(flag - CG * kEpiWarps) != p.epoch) __nanosleep(32);
+          __syncwarp();
+          fence_proxy_async_all();
+        }
+        gemm_epilogue_tile<BN, EPI>(p, &tmC, t_row, row0, lane, n_blk * BN, par, my_staging, sbuf, u.part <= 0);
+        if (u.part >= 0 && u.part < split - 1) {
+          if (lane == 0) {
+            tma_store_wait<0>();   // the reduce-adds of this part have been performed
+            fence_proxy_async_all();
+            __threadfence();
+            st_release_gpu(flag, p.epoch);
+          }
+          __syncwarp();
+        }
+      } else {
+        gemm_epilogue_tile<BN, EPI>(p, &tmC, t_row, row0, lane, n_blk * BN, par, my_staging, sbuf);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
