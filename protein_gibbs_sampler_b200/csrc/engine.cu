@@ -144,7 +144,7 @@ static int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const Ge
   if (EPI == EPI_RESID_F32 && p.flags && g_gemm_split) {
     // partly-filled last wave: cut its tiles along K so that the idle groups take a share (gemm_work_unit)
     const int tiles = m_tiles * n_tiles, rem = tiles % groups;
-    if (tiles > groups && rem) q.split = std::min({groups / rem, 4, p.K / kBK / 4, kSplitFlagInts / (rem * CG * kEpiWarps)});
+    if (tiles > groups && rem) q.split = std::min({groups / rem, 4, p.K / kBK / 32, kSplitFlagInts / (rem * CG * kEpiWarps)});
     if (q.split < 2) q.split = 1;
   }
   cudaLaunchConfig_t cfg{};

@@ -142,6 +142,17 @@ __device__ __forceinline__ int ld_acquire_gpu(const int32_t* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Bounded spin on a flag in global memory: a protocol bug traps (launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void spin_until_equal(const int32_t* p, int want) {
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(p) != want) {
+    __nanosleep(40);
+    if (++spins > (1u << 25)) {
+      printf("pgibbs: GEMM split flag wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void st_release_gpu(int32_t* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -384,7 +395,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // K-split tile: this warp's chunks are added after the same warp of the previous part has added its own
         int32_t* flag = p.flags + ((u.slot * split + (u.part > 0 ? u.part : 0)) * CG + rank) * kEpiWarps + ew;
         if (u.part > 0) {
-          if (lane == 0) while (ld_acquire_gpu(flag - CG * kEpiWarps) != p.epoch) __nanosleep(32);
+          if (lane == 0) spin_until_equal(flag - CG * kEpiWarps, p.epoch);
           __syncwarp();
           fence_proxy_async_all();
         }
