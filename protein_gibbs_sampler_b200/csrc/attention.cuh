@@ -75,6 +75,9 @@ constexpr int kAttnBK = 64;   // keys per smem chunk
 
 template <int DH, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32) attention_kernel(AttnParams p) {
+  // programmatic dependent launch (no-ops in a normal launch): wait for the previous kernel, release the next one
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   constexpr int kAttnBQ = 16 * NWARPS;  // queries per CTA
   constexpr int NT_ = NWARPS * 32;
   constexpr int LDS = DH + 8;          // padded row (halfs): 16-byte pad keeps ldmatrix conflict-free

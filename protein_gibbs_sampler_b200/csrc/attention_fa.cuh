@@ -151,6 +151,8 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();               // set-up above overlaps the previous kernel's tail (programmatic dependent launch)
+  pdl_launch_dependents();
 
   const int trace_slot = warp == 1 ? 0 : warp == 4 ? 1 : warp == 3 ? 2 : warp == 8 ? 3 : -1;
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_slot >= 0;

@@ -118,7 +118,21 @@ static int g_num_sms = 0;
 // A GEMM's tiling: tile width and whether a CTA pair (cta_group::2, 256-row tiles) computes it.
 // The B tensor map's box holds bn / cg rows.
 constexpr int kSplitFlagInts = 4096;  // K-split flags: >= 148 groups x 2 ranks x 8 epilogue warps
-static int g_gemm_split = 1;          // PGIBBS_GEMM_SPLIT=0 turns the last-wave K-split off (A/B measurements)
+static int g_gemm_split = 1;
+static int g_pdl = 1;                 // PGIBBS_PDL=0: plain stream-ordered launches
+
+// Launch with programmatic dependent launch allowed: the kernel must call pdl_wait() before it touches global memory.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}          // PGIBBS_GEMM_SPLIT=0 turns the last-wave K-split off (A/B measurements)
 
 struct GemmPlan {
   int bn = 256, cg = 2;
@@ -152,11 +166,13 @@ static int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const Ge
   cfg.blockDim = dim3(kGemmThreads);
   cfg.dynamicSmemBytes = gemm_smem_bytes(BN, CG);
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   CK(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, EPI, CG>, a, b, c, q));
   return 0;
 }
@@ -514,11 +530,10 @@ static int run_ln(pgibbs_engine* e, const float* x, const float* w, const float*
   ProfScope ps(e, "layernorm");
   const dim3 grid((rows + 7) / 8);
   const int vpl = (p.d / 4 + 31) / 32;  // float4 vectors per lane
-  if (vpl <= 3) layernorm_kernel<true, 3><<<grid, 256, 0, e->stream>>>(p);
-  else if (vpl <= 6) layernorm_kernel<true, 6><<<grid, 256, 0, e->stream>>>(p);
-  else if (vpl <= 10) layernorm_kernel<true, 10><<<grid, 256, 0, e->stream>>>(p);
-  else layernorm_kernel<true, kMaxVecPerLane><<<grid, 256, 0, e->stream>>>(p);
-  CK(cudaGetLastError());
+  if (vpl <= 3) CK(launch_pdl(layernorm_kernel<true, 3>, grid, dim3(256), 0, e->stream, p));
+  else if (vpl <= 6) CK(launch_pdl(layernorm_kernel<true, 6>, grid, dim3(256), 0, e->stream, p));
+  else if (vpl <= 10) CK(launch_pdl(layernorm_kernel<true, 10>, grid, dim3(256), 0, e->stream, p));
+  else CK(launch_pdl(layernorm_kernel<true, kMaxVecPerLane>, grid, dim3(256), 0, e->stream, p));
   return 0;
 }
 
@@ -528,8 +543,7 @@ static int run_gather_f32(pgibbs_engine* e, const float* x, float* out, int rows
   p.x = x; p.w = nullptr; p.b = nullptr; p.out = out; p.rows_out = rows; p.d = e->cfg.embed_dim; p.eps = e->ln_eps;
   p.sched = gather; p.iter = iter; p.T = e->T; p.identity = 1;
   ProfScope ps(e, "layernorm");
-  layernorm_kernel<false, kMaxVecPerLane><<<(rows + 7) / 8, 256, 0, e->stream>>>(p);
-  CK(cudaGetLastError());
+  CK(launch_pdl(layernorm_kernel<false, kMaxVecPerLane>, dim3((rows + 7) / 8), dim3(256), 0, e->stream, p));
   return 0;
 }
 
@@ -544,21 +558,21 @@ static int launch_attention(const AttnParams& p, int groups, int H, int hd, cuda
   const int nq = p.T - p.q_begin;  // query rows handled by this launch
   if (nq <= 16 && hd == 64) {      // a few trailing rows (tail of the tcgen05 kernel): one warp per (group, head)
     dim3 grid(1, H, groups);
-    attention_kernel<64, 1><<<grid, 32, 0, st>>>(p);
+    CK(launch_pdl(attention_kernel<64, 1>, grid, dim3(32), 0, st, p));
   } else if (nq <= 32) {  // short groups (MSA column attention over R <= 32 rows): 2 warps = 32 queries per CTA
     dim3 grid((nq + 31) / 32, H, groups);
     switch (hd) {
-      case 16: attention_kernel<16, 2><<<grid, 64, 0, st>>>(p); break;
-      case 32: attention_kernel<32, 2><<<grid, 64, 0, st>>>(p); break;
-      case 64: attention_kernel<64, 2><<<grid, 64, 0, st>>>(p); break;
+      case 16: CK(launch_pdl(attention_kernel<16, 2>, grid, dim3(64), 0, st, p)); break;
+      case 32: CK(launch_pdl(attention_kernel<32, 2>, grid, dim3(64), 0, st, p)); break;
+      case 64: CK(launch_pdl(attention_kernel<64, 2>, grid, dim3(64), 0, st, p)); break;
       default: return fail("unsupported head_dim %d (16, 32, 64)", hd);
     }
   } else {
     dim3 grid((nq + 63) / 64, H, groups);
     switch (hd) {
-      case 16: attention_kernel<16, 4><<<grid, 128, 0, st>>>(p); break;
-      case 32: attention_kernel<32, 4><<<grid, 128, 0, st>>>(p); break;
-      case 64: attention_kernel<64, 4><<<grid, 128, 0, st>>>(p); break;
+      case 16: CK(launch_pdl(attention_kernel<16, 4>, grid, dim3(128), 0, st, p)); break;
+      case 32: CK(launch_pdl(attention_kernel<32, 4>, grid, dim3(128), 0, st, p)); break;
+      case 64: CK(launch_pdl(attention_kernel<64, 4>, grid, dim3(128), 0, st, p)); break;
       default: return fail("unsupported head_dim %d (16, 32, 64)", hd);
     }
   }
@@ -598,8 +612,7 @@ static int launch_attention_fa(const CUtensorMap& qkv3, const CUtensorMap& ctx3,
   AttnFaParams p{T, H, n_seq, any_tail ? T / 128 : (T + 127) / 128, g_fa_trace, g_attn_stagger,
                  in_kernel ? tail : 0, qkv, ctx};
   const int n_items = n_seq * H * ((p.n_tiles + 1) / 2);
-  attention_fa_kernel<<<std::min(g_num_sms, n_items), kFaThreads, kFaSmemBytes, st>>>(qkv3, ctx3, p);
-  CK(cudaGetLastError());
+  CK(launch_pdl(attention_fa_kernel, dim3(std::min(g_num_sms, n_items)), dim3(kFaThreads), kFaSmemBytes, st, qkv3, ctx3, p));
   if (any_tail && !in_kernel) {
     const int d = H * 64;
     AttnParams tp{qkv, ctx, T, 3 * d, d, d, 2 * d, 1, 0, 1, T, T - tail};
@@ -626,8 +639,7 @@ static int run_msa_row_attention(pgibbs_engine* e) {
       configured = smem;
     }
     dim3 grid((e->T + 127) / 128, c.heads, e->B);
-    msa_row_attention_tc_kernel<<<grid, kMrThreads, smem, e->stream>>>(e->m_qkv3, e->m_qkv3_keys, e->m_ctx3, p);
-    CK(cudaGetLastError());
+    CK(launch_pdl(msa_row_attention_tc_kernel, grid, dim3(kMrThreads), smem, e->stream, e->m_qkv3, e->m_qkv3_keys, e->m_ctx3, p));
     return 0;
   }
   if (const char* m = launch_msa_row_attention(e->qkv, e->ctx, e->scores, e->B, e->R, e->T, c.heads, hd, e->stream))
@@ -671,8 +683,7 @@ static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int it
     p.x = e->x; p.n_seq = e->n_seq; p.T = e->T; p.d = d; p.rows_per_msa = e->R;
     p.mask_idx = c.mask_idx; p.token_dropout = c.token_dropout; p.eps = e->ln_eps;
     ProfScope ps(e, "embed");
-    embed_kernel<<<(M + 7) / 8, 256, 0, st>>>(p);
-    CK(cudaGetLastError());
+    CK(launch_pdl(embed_kernel, dim3((M + 7) / 8), dim3(256), 0, st, p));
   }
   const int n_layers = e->layer_limit >= 0 ? std::min(e->layer_limit, c.layers) : c.layers;
   for (int li = 0; li < n_layers; ++li) {
@@ -710,8 +721,8 @@ static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int it
       TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->g_qkv, e->m_h, l.m_wqkv, q));
       if (c.arch == PGIBBS_ARCH_ESM1) {  // the extra row of every sequence becomes the learned bias key / value
         ProfScope ps(e, "bias_kv");
-        bias_kv_kernel<<<(e->n_seq * d + 255) / 256, 256, 0, st>>>(e->qkv, l.bias_k, l.bias_v, e->n_seq, e->T, d);
-        CK(cudaGetLastError());
+        CK(launch_pdl(bias_kv_kernel, dim3((e->n_seq * d + 255) / 256), dim3(256), 0, st, e->qkv, l.bias_k, l.bias_v,
+                      e->n_seq, e->T, d));
       }
       TRY(run_attention(e));
       TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->g_o, e->m_ctx, l.m_wo, gp(M, d, d, l.bo, e->x, d)));
@@ -758,8 +769,7 @@ static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int it
     }
     const int grid = std::min(g_num_sms, (rows + 7) / 8);
     ProfScope ps(e, "head_sample");
-    head_sample_kernel<<<grid, 256, p.emb_in_smem ? emb_bytes : 0, st>>>(p);
-    CK(cudaGetLastError());
+    CK(launch_pdl(head_sample_kernel, dim3(grid), dim3(256), p.emb_in_smem ? emb_bytes : 0, st, p));
   }
   return 0;
 }
@@ -805,9 +815,8 @@ static int run_iters(pgibbs_engine* e, int first_iter, int num_iters, int64_t bu
       Schedule ms = s;
       if (single) ms.seq_offset = mask_row;
       ProfScope ps(e, "mask_scatter");
-      mask_scatter_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, e->stream>>>(
-          e->tokens, n_chains, e->T, ms, it, e->cfg.mask_idx);
-      CK(cudaGetLastError());
+      CK(launch_pdl(mask_scatter_kernel, dim3(static_cast<unsigned>((rows + 255) / 256)), dim3(256), 0, e->stream,
+                    e->tokens, n_chains, e->T, ms, it, e->cfg.mask_idx));
     }
     const int k_eff = (it < burnin || top_k <= 0 || top_k > n_valid) ? n_valid : top_k;
     TRY(forward(e, s, n_chains, it, true, k_eff, temperature, n_valid, nullptr));
@@ -835,6 +844,7 @@ int pgibbs_create(const pgibbs_model_config* cfg, int32_t device_id, pgibbs_engi
   g_num_sms = prop.multiProcessorCount;
   if (const char* f = getenv("PGIBBS_GEMM_CG")) g_force_cg = atoi(f);
   if (const char* f = getenv("PGIBBS_GEMM_SPLIT")) g_gemm_split = atoi(f);
+  if (const char* f = getenv("PGIBBS_PDL")) g_pdl = atoi(f);
   if (cfg->embed_dim % cfg->heads) return fail("embed_dim %% heads != 0");
   if (cfg->embed_dim % 64 || cfg->ffn_dim % 64) return fail("embed_dim and ffn_dim must be multiples of 64");
   if (cfg->embed_dim > kMaxVecPerLane * 128) return fail("embed_dim %d too large (max %d)", cfg->embed_dim, kMaxVecPerLane * 128);

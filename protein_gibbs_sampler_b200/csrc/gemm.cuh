@@ -298,6 +298,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if constexpr (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above is local set-up and may overlap the previous kernel's tail; operands and outputs are not
+  pdl_wait();
+  pdl_launch_dependents();
 
   // Producer and MMA warps: the WHOLE warp walks the tile schedule (barrier waits, address arithmetic) and one
   // elected lane issues the TMA / tcgen05 instructions.  Under a `lane == 0` branch the operands are per-thread

@@ -19,6 +19,9 @@ namespace pg {
 template <int DH>
 __global__ void __launch_bounds__(128) msa_row_scores_kernel(const __half* __restrict__ qkv, float* __restrict__ scores,
                                                              int R, int C, int H, int ld, int k_off) {
+  // programmatic dependent launch (no-ops in a normal launch): wait for the previous kernel, release the next one
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   constexpr int LDS = DH + 8, CH = DH / 8, KS = DH / 16;
   __shared__ __align__(16) __half sQ[2][64 * LDS];
   __shared__ __align__(16) __half sK[2][64 * LDS];
@@ -92,6 +95,9 @@ template <int DH>
 __global__ void __launch_bounds__(128) msa_row_pv_kernel(const __half* __restrict__ qkv, const float* __restrict__ scores,
                                                          __half* __restrict__ ctx, int R, int C, int H, int ld,
                                                          int ldc, int v_off, int rows_per_group, int Cpad) {
+  // programmatic dependent launch (no-ops in a normal launch): wait for the previous kernel, release the next one
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   constexpr int LDS = DH + 8, CH = DH / 8, NT = DH / 8;
   extern __shared__ __align__(16) unsigned char msa_smem[];
   const int ldp = Cpad + 8;
@@ -187,6 +193,9 @@ __global__ void __launch_bounds__(128) msa_row_pv_kernel(const __half* __restric
 // loop: R <= 32).  Token r of group s = (b, c) lives in activation row (b*R + r)*C + c.
 template <int HG>
 __global__ void __launch_bounds__(64 * HG) msa_col_attention_kernel(AttnParams p) {
+  // programmatic dependent launch (no-ops in a normal launch): wait for the previous kernel, release the next one
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   constexpr int DH = 64, LDS = DH + 8, KS = DH / 16, NT = DH / 8;
   extern __shared__ __align__(16) unsigned char col_smem[];
   __half* sQ = reinterpret_cast<__half*>(col_smem);  // [HG][32 * LDS]

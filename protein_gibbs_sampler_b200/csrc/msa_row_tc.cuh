@@ -75,6 +75,8 @@ msa_row_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();               // set-up above overlaps the previous kernel's tail (programmatic dependent launch)
+  pdl_launch_dependents();
   const uint32_t tS = tmem_base, tO = tmem_base + 256;  // S / P: columns [0, NK); O: 2 x 64 columns
 
   if (warp == 0) {

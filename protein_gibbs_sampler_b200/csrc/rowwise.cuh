@@ -33,6 +33,9 @@ struct Schedule {
 // ---------------------------------------------------------------------------------------------
 __global__ void mask_scatter_kernel(int32_t* __restrict__ tokens, int n_chains, int T, Schedule s, int iter,
                                     int mask_idx) {
+  // programmatic dependent launch (no-ops in a normal launch): wait for the previous kernel, release the next one
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(n_chains) * s.P) return;
   const int chain = static_cast<int>(i / s.P), p = static_cast<int>(i % s.P);
@@ -63,6 +66,9 @@ struct EmbedParams {
 };
 
 __global__ void __launch_bounds__(256) embed_kernel(EmbedParams p) {
+  // programmatic dependent launch (no-ops in a normal launch): wait for the previous kernel, release the next one
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warps_per_block = blockDim.x >> 5;
   const int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -163,6 +169,10 @@ struct LnParams {
 // baked in, measured at d = 1280).
 template <bool OUT_F16, int VPL>
 __global__ void __launch_bounds__(256, VPL <= 10 ? 4 : 2) layernorm_kernel(LnParams p) {
+  // programmatic dependent launch (no-ops in a normal launch): wait for the kernel that wrote x, then let the next
+  // kernel's blocks be scheduled as this one's finish
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warps_per_block = blockDim.x >> 5;
   const int orow = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -227,6 +237,9 @@ __global__ void __launch_bounds__(256, VPL <= 10 ? 4 : 2) layernorm_kernel(LnPar
 // ---------------------------------------------------------------------------------------------
 __global__ void bias_kv_kernel(__half* __restrict__ qkv, const float* __restrict__ bias_k,
                                const float* __restrict__ bias_v, int n_seq, int T, int d) {
+  // programmatic dependent launch (no-ops in a normal launch): wait for the previous kernel, release the next one
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_seq * d) return;
   const int seq = i / d, c = i % d;
@@ -388,6 +401,9 @@ __global__ void __launch_bounds__(256) head_sample_kernel(HeadParams p) {
     for (int i = threadIdx.x; i < (p.V * p.d) >> 2; i += blockDim.x) dst[i] = __ldg(src + i);
     __syncthreads();
   }
+  // programmatic dependent launch: staging the (constant) projection table above overlaps the previous kernel
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const float* E = p.emb_in_smem ? s_emb : p.emb;
   const int nvec = p.d >> 2;
   for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < p.rows;

@@ -75,6 +75,10 @@ def report(name, ms, flops, note):
 
 
 want = set(sys.argv[1:]) or {"c2", "c3", "c4", "c5"}
+if "c1" in want:   # launch-bound shapes: BASELINE config 1 geometry and single-chain runs (pgen_msa_revised's regime)
+    single("C1 esm2_t6_8M, 2 x L25 (on the GPU)", models.ESM2_t6_8M(), 2, 25, 0, float("inf"), 2, iters=50, warm=5)
+    single("   ESM-1b 650M, 1 x L256", models.ESM1b(), 1, 256, 0, float("inf"), 25, iters=20, warm=3)
+    msa("   MSA-1b, 1 MSA x 32 rows x L128", 1, 32, 128, 12, iters=20, warm=3)
 if "c2" in want:
     single("C2 ESM-1b 650M, 64 x L256, top_k 3", models.ESM1b(), 64, 256, 3, 0, 0)
 if "c3" in want:
