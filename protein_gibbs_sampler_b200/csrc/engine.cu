@@ -120,6 +120,8 @@ static int g_num_sms = 0;
 constexpr int kSplitFlagInts = 4096;  // K-split flags: >= 148 groups x 2 ranks x 8 epilogue warps
 static int g_gemm_split = 1;
 static int g_pdl = 1;                 // PGIBBS_PDL=0: plain stream-ordered launches
+static int g_graph = 1;               // PGIBBS_GRAPH=0: every iteration is launched kernel by kernel
+constexpr int kGraphMinIters = 16;    // shorter runs do not pay for capture + instantiation (~1 ms)
 
 // Launch with programmatic dependent launch allowed: the kernel must call pdl_wait() before it touches global memory.
 template <typename... KArgs, typename... Args>
@@ -326,7 +328,11 @@ struct pgibbs_engine {
   int32_t* identity_pos = nullptr;  // 0..T-1 (forward_logits)
   // last-wave K-split of the residual GEMMs (gemm.cuh: gemm_work_unit): ordering flags, launch counter
   int32_t* split_flags = nullptr;
-  int split_epoch = 0;
+  // CUDA-graph replay of the iteration loop: the iteration index lives on the device (Schedule::iter_dev)
+  int32_t* iter_dev = nullptr;
+  bool dev_iter = false;      // forward() is being issued in device-iteration mode
+  int run_top_k = 0;          // the caller's top_k / burn-in for that mode
+  int64_t run_burnin = 0;
   // scoring pass (pgibbs_score): per-slot target ids in, log-probabilities out; live only during that call
   int32_t* sc_targets = nullptr;
   float* sc_logp = nullptr;
@@ -549,7 +555,7 @@ static int run_gather_f32(pgibbs_engine* e, const float* x, float* out, int rows
 
 static int run_gemm(pgibbs_engine* e, const char* name, int epi, GemmPlan g, const CUtensorMap& a,
                     const CUtensorMap& b, GemmParams p) {
-  if (epi == EPI_RESID_F32) { p.flags = e->split_flags; p.epoch = ++e->split_epoch; }
+  if (epi == EPI_RESID_F32) p.flags = e->split_flags;
   ProfScope ps(e, name);
   return launch_gemm(epi, g, a, b, p, e->stream);
 }
@@ -664,8 +670,10 @@ static GemmParams gp(int M, int N, int K, const float* bias, void* out, int ldo)
 
 // One transformer forward over the resident tokens.  `sched`: rows the LM head is evaluated on (chain-major);
 // sampling writes tokens when `sample` is set, logits rows are stored when `logits_out` is non-null.
-static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int iter, bool sample, int k_eff,
+static int forward(pgibbs_engine* e, const Schedule& sched_in, int n_chains, int iter, bool sample, int k_eff,
                    float temperature, int n_valid, float* logits_out) {
+  Schedule sched = sched_in;
+  if (e->dev_iter) sched.iter_dev = e->iter_dev;   // `iter` / `k_eff` are ignored by the kernels in this mode
   const auto& c = e->cfg;
   const int d = c.embed_dim, F = c.ffn_dim, M = e->M, hd = d / c.heads;
   cudaStream_t st = e->stream;
@@ -754,7 +762,9 @@ static int forward(pgibbs_engine* e, const Schedule& sched, int n_chains, int it
     p.rows = rows; p.d = d; p.V = c.vocab; p.T = e->T; p.eps = e->ln_eps;
     p.sched = sched; p.iter = iter;
     p.valid_ids = e->valid_dev; p.n_valid = n_valid; p.top_k = k_eff; p.temperature = temperature;
-    p.noise = (sample && e->noise) ? e->noise + static_cast<int64_t>(iter) * rows * e->noise_stride : nullptr;
+    p.noise = (sample && e->noise) ? e->noise + (e->dev_iter ? 0 : static_cast<int64_t>(iter) * rows * e->noise_stride)
+                                   : nullptr;
+    p.top_k_raw = e->run_top_k; p.burnin = e->run_burnin;
     p.noise_stride = e->noise_stride;
     p.seed = e->seed;
     p.rng_row_offset = e->rng_chain_offset * sched.P;
@@ -810,17 +820,60 @@ static int run_iters(pgibbs_engine* e, int first_iter, int num_iters, int64_t bu
   if (e->noise && e->noise_numel < static_cast<int64_t>(first_iter + num_iters) * rows * e->noise_stride)
     return fail("replay noise too short for the requested iterations");
   Schedule s{e->positions, e->iter_stride, e->chain_stride, e->P, single ? e->R : 1, single ? target_row : 0};
-  for (int it = first_iter; it < first_iter + num_iters; ++it) {
+  auto one_iteration = [&](int it) -> int {
     if (mask_flag) {
       Schedule ms = s;
       if (single) ms.seq_offset = mask_row;
+      if (e->dev_iter) ms.iter_dev = e->iter_dev;
       ProfScope ps(e, "mask_scatter");
       CK(launch_pdl(mask_scatter_kernel, dim3(static_cast<unsigned>((rows + 255) / 256)), dim3(256), 0, e->stream,
                     e->tokens, n_chains, e->T, ms, it, e->cfg.mask_idx));
     }
     const int k_eff = (it < burnin || top_k <= 0 || top_k > n_valid) ? n_valid : top_k;
     TRY(forward(e, s, n_chains, it, true, k_eff, temperature, n_valid, nullptr));
+    if (e->dev_iter) CK(launch_pdl(advance_iter_kernel, dim3(1), dim3(1), 0, e->stream, e->iter_dev));
+    return 0;
+  };
+  // Long runs: the first iteration is launched kernel by kernel with the iteration index on the device, the same
+  // launches are then captured once into a CUDA graph, and the graph is replayed for the remaining iterations (one
+  // driver call per iteration instead of ~270; the kernels read the iteration from Schedule::iter_dev).
+  if (g_graph && !e->prof && num_iters >= kGraphMinIters) {
+    e->dev_iter = true; e->run_top_k = top_k; e->run_burnin = burnin;
+    struct Reset { pgibbs_engine* e; ~Reset() { e->dev_iter = false; } } reset{e};
+    set_iter_kernel<<<1, 1, 0, e->stream>>>(e->iter_dev, first_iter);
+    CK(cudaGetLastError());
+    TRY(one_iteration(first_iter));   // also finishes every lazy one-time configuration outside the capture
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool ok = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    const int64_t counted = e->launches;
+    int64_t per_iter = 0;
+    if (ok) {
+      const int rc = one_iteration(first_iter + 1);   // recorded, not run
+      per_iter = e->launches - counted;
+      e->launches = counted;
+      const cudaError_t ce = cudaStreamEndCapture(e->stream, &graph);
+      ok = rc == 0 && ce == cudaSuccess && graph != nullptr;
+      if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    }
+    int done = 1;
+    if (ok) {
+      for (; done < num_iters; ++done) {
+        if (cudaGraphLaunch(exec, e->stream) != cudaSuccess) { ok = false; break; }
+        e->launches += per_iter;
+      }
+    }
+    if (exec) cudaGraphExecDestroy(exec);
+    if (graph) cudaGraphDestroy(graph);
+    if (!ok) {
+      (void)cudaGetLastError();
+      static bool warned = false;
+      if (!warned) { fprintf(stderr, "pgibbs: CUDA graph capture unavailable, launching kernel by kernel\n"); warned = true; }
+      for (; done < num_iters; ++done) TRY(one_iteration(first_iter + done));
+    }
+    return 0;
   }
+  for (int it = first_iter; it < first_iter + num_iters; ++it) TRY(one_iteration(it));
   return 0;
 }
 
@@ -845,6 +898,7 @@ int pgibbs_create(const pgibbs_model_config* cfg, int32_t device_id, pgibbs_engi
   if (const char* f = getenv("PGIBBS_GEMM_CG")) g_force_cg = atoi(f);
   if (const char* f = getenv("PGIBBS_GEMM_SPLIT")) g_gemm_split = atoi(f);
   if (const char* f = getenv("PGIBBS_PDL")) g_pdl = atoi(f);
+  if (const char* f = getenv("PGIBBS_GRAPH")) g_graph = atoi(f);
   if (cfg->embed_dim % cfg->heads) return fail("embed_dim %% heads != 0");
   if (cfg->embed_dim % 64 || cfg->ffn_dim % 64) return fail("embed_dim and ffn_dim must be multiples of 64");
   if (cfg->embed_dim > kMaxVecPerLane * 128) return fail("embed_dim %d too large (max %d)", cfg->embed_dim, kMaxVecPerLane * 128);
@@ -862,7 +916,8 @@ int pgibbs_create(const pgibbs_model_config* cfg, int32_t device_id, pgibbs_engi
   }
   e->stream = e->own_stream;
   if (cudaMalloc(&e->split_flags, kSplitFlagInts * sizeof(int32_t)) != cudaSuccess ||
-      cudaMemset(e->split_flags, 0, kSplitFlagInts * sizeof(int32_t)) != cudaSuccess) {
+      cudaMemset(e->split_flags, 0, kSplitFlagInts * sizeof(int32_t)) != cudaSuccess ||
+      cudaMalloc(&e->iter_dev, sizeof(int32_t)) != cudaSuccess) {
     pgibbs_destroy(e);
     return fail("cudaMalloc of the GEMM split flags failed");
   }
@@ -884,6 +939,7 @@ int pgibbs_destroy(pgibbs_engine* e) {
   cudaFree(e->sc_targets);
   cudaFree(e->sc_logp);
   cudaFree(e->split_flags);
+  cudaFree(e->iter_dev);
   for (auto& t : e->prof_pending) { cudaEventDestroy(std::get<1>(t)); cudaEventDestroy(std::get<2>(t)); }
   for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -1239,7 +1295,6 @@ int pgibbs_op_gemm(int32_t device_id, const float* A, const float* B, const floa
   float *dA = nullptr, *dB = nullptr, *dbias = nullptr, *dC32 = nullptr;
   __half *hA = nullptr, *hB = nullptr, *dC16 = nullptr;
   int32_t* dflags = nullptr;
-  int epoch = 0;
   int rc = 0;
   cudaStream_t st = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -1264,7 +1319,7 @@ int pgibbs_op_gemm(int32_t device_id, const float* A, const float* B, const floa
     TRY(make_tmap_2d(&mb, hB, N, K, K, plan.b_box()));
     GemmParams p = gp(M, N, K, dbias, out16 ? static_cast<void*>(dC16) : static_cast<void*>(dC32), N);
     p.flags = dflags;
-    auto launch_plan = [&]() -> int { p.epoch = ++epoch; return launch_gemm(epilogue, plan, ma, mb, p, st); };
+    auto launch_plan = [&]() -> int { return launch_gemm(epilogue, plan, ma, mb, p, st); };
     TRY(launch_plan());
     CK(cudaStreamSynchronize(st));
     if (out16) {

@@ -44,8 +44,9 @@ struct GemmParams {
   const float2* rope;   // [seq_len, head_dim/2] (cos, sin)
   // EPI_RESID_F32 only: K-split of the partly-filled last wave (see gemm_work_unit).  split <= 1: off.
   int split;            // parts each last-wave tile is cut into along K
-  int epoch;            // launch counter of the owner of `flags` (strictly increasing)
-  int32_t* flags;       // [last-wave tile][part][CTA rank][epilogue warp] = epoch once that warp's reduce-adds landed
+  int32_t* flags;       // [last-wave tile][part][CTA rank][epilogue warp]: 1 once that warp's reduce-adds have landed;
+                        // zero between launches (the one waiter of a flag clears it), so a launch captured in a
+                        // CUDA graph can be replayed as it is
 };
 
 constexpr int kBM = 128;
@@ -398,7 +399,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // K-split tile: this warp's chunks are added after the same warp of the previous part has added its own
         int32_t* flag = p.flags + ((u.slot * split + (u.part > 0 ? u.part : 0)) * CG + rank) * kEpiWarps + ew;
         if (u.part > 0) {
-          if (lane == 0) spin_until_equal(flag - CG * kEpiWarps, p.epoch);
+          if (lane == 0) {
+            spin_until_equal(flag - CG * kEpiWarps, 1);
+            *(flag - CG * kEpiWarps) = 0;   // this warp is the flag's only waiter: leave it clear for the next launch
+          }
           __syncwarp();
           fence_proxy_async_all();
         }
@@ -408,7 +412,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tma_store_wait<0>();   // the reduce-adds of this part have been performed
             fence_proxy_async_all();
             __threadfence();
-            st_release_gpu(flag, p.epoch);
+            st_release_gpu(flag, 1);
           }
           __syncwarp();
         }

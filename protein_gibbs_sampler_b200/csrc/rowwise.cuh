@@ -25,7 +25,17 @@ struct Schedule {
   long long iter_stride, chain_stride;
   int P;
   int seq_stride, seq_offset;
+  // Iteration index kept on the device (CUDA-graph replay of one captured iteration): when set, kernels read the
+  // iteration from here instead of their `iter` argument and advance_iter_kernel bumps it at the end of the iteration.
+  const int32_t* iter_dev;
 };
+
+__global__ void set_iter_kernel(int32_t* it, int value) { *it = value; }
+__global__ void advance_iter_kernel(int32_t* it) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  *it += 1;
+}
 
 // ---------------------------------------------------------------------------------------------
 // <mask> scatter: tokens[chain][pos] = mask_idx for every scheduled position.
@@ -39,6 +49,7 @@ __global__ void mask_scatter_kernel(int32_t* __restrict__ tokens, int n_chains, 
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i >= static_cast<long long>(n_chains) * s.P) return;
   const int chain = static_cast<int>(i / s.P), p = static_cast<int>(i % s.P);
+  if (s.iter_dev) iter = *s.iter_dev;
   const int pos = s.positions[iter * s.iter_stride + chain * s.chain_stride + p];
   tokens[(static_cast<long long>(chain) * s.seq_stride + s.seq_offset) * T + pos] = mask_idx;
 }
@@ -181,7 +192,8 @@ __global__ void __launch_bounds__(256, VPL <= 10 ? 4 : 2) layernorm_kernel(LnPar
   if (p.sched.positions) {
     const int chain = orow / p.sched.P, q = orow % p.sched.P;
     srow = (static_cast<long long>(chain) * p.sched.seq_stride + p.sched.seq_offset) * p.T +
-           p.sched.positions[p.iter * p.sched.iter_stride + chain * p.sched.chain_stride + q];
+           p.sched.positions[(p.sched.iter_dev ? *p.sched.iter_dev : p.iter) * p.sched.iter_stride +
+                             chain * p.sched.chain_stride + q];
   }
   const float4* in = reinterpret_cast<const float4*>(p.x + srow * p.d);
   const int nvec = p.d >> 2;
@@ -378,6 +390,8 @@ struct HeadParams {
   const int32_t* valid_ids;  // [n_valid] (device)
   int n_valid;
   int top_k;                 // effective k for this iteration (already resolved against burn-in), <= n_valid
+  int top_k_raw;             // with sched.iter_dev: the caller's top_k and burn-in, resolved per iteration on the device
+  long long burnin;
   float temperature;         // <= 0 : none
   const float* noise;        // replay: [rows, noise_stride] Exp(1) draws for this iteration, slot j <-> j-th largest
   int noise_stride;
@@ -477,11 +491,19 @@ __global__ void __launch_bounds__(256) head_sample_kernel(HeadParams p) {
     }
     if (!p.tokens) continue;
 
-    const int best_id = generate_step_warp(mine, extra, lane, row, p.iter, p.valid_ids, p.n_valid, p.top_k,
-                                           p.temperature, p.noise, p.noise_stride, p.seed, p.rng_row_offset);
+    // device-resident iteration (graph replay): the effective k and the noise slice follow from it
+    int iter = p.iter, top_k = p.top_k;
+    const float* noise = p.noise;
+    if (p.sched.iter_dev) {
+      iter = *p.sched.iter_dev;
+      top_k = (iter < p.burnin || p.top_k_raw <= 0 || p.top_k_raw > p.n_valid) ? p.n_valid : p.top_k_raw;
+      if (noise) noise += static_cast<long long>(iter) * p.rows * p.noise_stride;
+    }
+    const int best_id = generate_step_warp(mine, extra, lane, row, iter, p.valid_ids, p.n_valid, top_k,
+                                           p.temperature, noise, p.noise_stride, p.seed, p.rng_row_offset);
     if (lane == 0) {
       const int chain = row / p.sched.P, slot = row % p.sched.P;
-      const int32_t* plist = p.sched.positions + p.iter * p.sched.iter_stride + chain * p.sched.chain_stride;
+      const int32_t* plist = p.sched.positions + iter * p.sched.iter_stride + chain * p.sched.chain_stride;
       const int pos = plist[slot];
       bool write = true;
       if (p.skip_dup_writes) {
