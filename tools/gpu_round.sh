@@ -25,3 +25,7 @@ timeout 600 ncu --set full --clock-control none --import-source on --profile-fro
     -k regex:gemm_tcgen05 -s 8 -c 4 -o $OUT/${TAG}_gemm python bench.py --steps 1 --warmup 3 --no-cpu-baseline \
     > $OUT/${TAG}_ncu_gemm.log 2>&1
 echo "ncu full exit $?"; ls -la $OUT
+
+echo "== per-config table"
+timeout 900 python tools/config_bench.py c1 c2 c3 c4 c5 2>&1 | grep -v warning > $OUT/${TAG}_config_bench.txt
+cat $OUT/${TAG}_config_bench.txt
