@@ -381,3 +381,64 @@ def test_graph_replay_equals_kernel_by_kernel(arch, rng, monkeypatch):
             outs.append(s.generate(5, seq, batch_size=3, in_order=(arch == "esm1"), **kw))
     assert outs[0] == outs[1]
     assert len(set(outs[1])) > 1   # the chains did move
+
+
+# ----------------------------------------------------------------- full-size properties of the other BASELINE configs
+def _full_size_properties(sampler, toks, plan, rows_per_unit, valid_hi, units_sub, **run_kw):
+    """Determinism, only scheduled positions change, only valid residues are written, and a sub-batch of chains /
+    MSAs with its slice of the schedule reproduces itself (independent Markov chains: what sharding across GPUs
+    relies on)."""
+    def run(tokens, pl):
+        torch.manual_seed(7)    # the device RNG seed is drawn from torch's generator
+        return sampler.run_plan(tokens, pl, mask=True, **run_kw)
+
+    n_chains = toks.shape[0] * rows_per_unit
+    a = run(toks, plan)
+    assert torch.equal(a, run(toks, plan))
+    flat_in, flat_out = toks.reshape(n_chains, -1), a.reshape(n_chains, -1)
+    touched = torch.zeros_like(flat_in, dtype=torch.bool)
+    for it in range(plan.n_iters):
+        for c in range(n_chains):
+            touched[c, plan.targets(it, c)] = True
+    assert torch.equal(flat_out[~touched], flat_in[~touched])
+    assert bool(((flat_out[touched] >= 4) & (flat_out[touched] <= valid_hi)).all())
+    assert not torch.equal(flat_out[touched], flat_in[touched])
+    sub = run(toks[:units_sub], plan.slice_chains(0, units_sub * rows_per_unit, n_chains))
+    assert torch.equal(sub, a[:units_sub])
+    return a
+
+
+def test_full_size_properties_config3_msa():
+    """BASELINE config 3 geometry: MSA-1b, 16 MSAs x 32 rows x L=128, 10 % of the positions per row and iteration."""
+    from protein_gibbs_sampler_b200 import models
+    from protein_gibbs_sampler_b200.esm_msa_sampler import ESM_MSA_sampler
+    rng = random.Random(1)
+    rows = ["".join(rng.choice("ACDEFGHIKLMNPQRSTVWY") for _ in range(128)) for _ in range(32)]
+    m = models.ESM_MSA1(seed=0)
+    s = ESM_MSA_sampler(m, device="cuda:0", rng="device")
+    toks = m.batch_converter([[(str(i), x) for i, x in enumerate(rows)]] * 16)[2]
+    idx, _ = s.calculate_indexes(None, 0, 128, False)
+    random.seed(3)
+    plan, _ = s.plan_positions(16, 32, idx, -1, 12, False, 2)
+    out = _full_size_properties(s, toks, plan, 32, 30, 4, top_k=0, temperature=None, burnin=float("inf"))
+    assert out.shape == (16, 32, 129)
+
+
+@pytest.mark.parametrize("name,B,L,P,top_k", [("esm2_t33_650M", 64, 512, 0, 5), ("esm1b", 16, 1022, 51, 0)])
+def test_full_size_properties_config4_and_5_shards(name, B, L, P, top_k):
+    """Per-GPU shards of BASELINE configs 4 (ESM-2 650M, 64 of 512 chains x L=512, top_k 5) and 5 (ESM-1b, 16 of 128
+    chains x L=1022 = the longest sequence the learned positions allow, 5 % of the positions per iteration)."""
+    from protein_gibbs_sampler_b200 import models
+    from protein_gibbs_sampler_b200.esm_sampler import ESM_sampler
+    rng = random.Random(1)
+    seeds = ["".join(rng.choice("ACDEFGHIKLMNPQRSTVWY") for _ in range(L)) for _ in range(B)]
+    m = (models.ESM2_t33_650M if name == "esm2_t33_650M" else models.ESM1b)(seed=0)
+    s = ESM_sampler(m, device="cuda:0", rng="device")
+    toks = m.batch_converter([(str(i), x) for i, x in enumerate(seeds)])[2]
+    idx, last_i = s.calculate_indexes(None, 0, L, False)
+    if not P:   # config 4 resamples every position; keep a fixed subset here so that some positions must stay put
+        idx = sorted(random.Random(2).sample(list(idx), 64))
+    random.seed(3)
+    plan, _ = s.plan_positions(B, idx, last_i, P, False, 2)
+    out = _full_size_properties(s, toks[:, None], plan, 1, 23, B // 4, top_k=top_k, temperature=None, burnin=1)
+    assert out.shape == (B, 1, L + 2)
