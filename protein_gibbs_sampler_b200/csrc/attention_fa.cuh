@@ -51,6 +51,7 @@ struct AttnFaParams {
   int tail_rows;
   const __half* qkv;  // [n_seq*T, 3*H*64]
   __half* ctx;        // [n_seq*T, H*64]
+  int reverse;        // walk the (sequence, head) items from the last one down (see pgibbs_engine::zigzag)
 };
 constexpr int kFaTraceCap = 2048;
 
@@ -164,7 +165,8 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   // item -> (pair, seq, head): pair-major so that every CTA gets the same mix of full and partial pairs
   auto decode = [&](int item, int& pair, int& seq, int& head) {
     pair = item / n_sh;
-    const int r = item - pair * n_sh;
+    int r = item - pair * n_sh;
+    if (p.reverse) r = n_sh - 1 - r;
     seq = r / p.H;
     head = r - seq * p.H;
   };

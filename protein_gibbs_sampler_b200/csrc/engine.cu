@@ -121,6 +121,7 @@ constexpr int kSplitFlagInts = 4096;  // K-split flags: >= 148 groups x 2 ranks 
 static int g_gemm_split = 1;
 static int g_pdl = 1;                 // PGIBBS_PDL=0: plain stream-ordered launches
 static int g_graph = 1;               // PGIBBS_GRAPH=0: every iteration is launched kernel by kernel
+static int g_zigzag = 1;              // PGIBBS_ZIGZAG=0: every kernel walks its rows in ascending order
 constexpr int kGraphMinIters = 16;    // shorter runs do not pay for capture + instantiation (~1 ms)
 
 // Launch with programmatic dependent launch allowed: the kernel must call pdl_wait() before it touches global memory.
@@ -328,6 +329,11 @@ struct pgibbs_engine {
   int32_t* identity_pos = nullptr;  // 0..T-1 (forward_logits)
   // last-wave K-split of the residual GEMMs (gemm.cuh: gemm_work_unit): ordering flags, launch counter
   int32_t* split_flags = nullptr;
+  // Zigzag: consecutive kernels of the forward walk the token rows in opposite directions, so that each one starts
+  // on the rows its producer wrote last -- the part of a 40-170 MB activation that is still in the 126 MB L2 --
+  // instead of on the rows that have just been evicted (ascending order everywhere is the LRU worst case).
+  int zigzag = 0;
+  int next_dir() { if (!g_zigzag) return 0; zigzag ^= 1; return zigzag; }
   // CUDA-graph replay of the iteration loop: the iteration index lives on the device (Schedule::iter_dev)
   int32_t* iter_dev = nullptr;
   bool dev_iter = false;      // forward() is being issued in device-iteration mode
@@ -533,6 +539,7 @@ static int run_ln(pgibbs_engine* e, const float* x, const float* w, const float*
   p.x = x; p.w = w; p.b = b; p.out = out; p.rows_out = rows; p.d = e->cfg.embed_dim; p.eps = e->ln_eps;
   if (gather) p.sched = *gather; else p.sched.positions = nullptr;
   p.iter = iter; p.T = e->T;
+  p.reverse = gather ? 0 : e->next_dir();
   ProfScope ps(e, "layernorm");
   const dim3 grid((rows + 7) / 8);
   const int vpl = (p.d / 4 + 31) / 32;  // float4 vectors per lane
@@ -556,6 +563,7 @@ static int run_gather_f32(pgibbs_engine* e, const float* x, float* out, int rows
 static int run_gemm(pgibbs_engine* e, const char* name, int epi, GemmPlan g, const CUtensorMap& a,
                     const CUtensorMap& b, GemmParams p) {
   if (epi == EPI_RESID_F32) p.flags = e->split_flags;
+  p.reverse = e->next_dir();
   ProfScope ps(e, name);
   return launch_gemm(epi, g, a, b, p, e->stream);
 }
@@ -604,7 +612,7 @@ static int attn_mode(int hd) {
 }
 // qkv: fused activation [n_seq*T, 3*H*64]; ctx: [n_seq*T, H*64].
 static int launch_attention_fa(const CUtensorMap& qkv3, const CUtensorMap& ctx3, const __half* qkv, __half* ctx,
-                               int n_seq, int T, int H, cudaStream_t st) {
+                               int n_seq, int T, int H, cudaStream_t st, int reverse = 0) {
   static bool configured = false;
   if (!configured) {
     CK(cudaFuncSetAttribute(attention_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
@@ -616,7 +624,7 @@ static int launch_attention_fa(const CUtensorMap& qkv3, const CUtensorMap& ctx3,
   const bool any_tail = g_attn_tail && T > 128 && tail > 0 && tail <= 16;
   const bool in_kernel = any_tail && tail <= 8 && g_attn_tail != 2;
   AttnFaParams p{T, H, n_seq, any_tail ? T / 128 : (T + 127) / 128, g_fa_trace, g_attn_stagger,
-                 in_kernel ? tail : 0, qkv, ctx};
+                 in_kernel ? tail : 0, qkv, ctx, reverse};
   const int n_items = n_seq * H * ((p.n_tiles + 1) / 2);
   CK(launch_pdl(attention_fa_kernel, dim3(std::min(g_num_sms, n_items)), dim3(kFaThreads), kFaSmemBytes, st, qkv3, ctx3, p));
   if (any_tail && !in_kernel) {
@@ -657,7 +665,8 @@ static int run_attention(pgibbs_engine* e) {
   const int d = e->cfg.embed_dim, H = e->cfg.heads, hd = d / H;
   ProfScope ps(e, "attention");
   const int mode = attn_mode(hd);
-  if (mode == 2) return launch_attention_fa(e->m_qkv3, e->m_ctx3, e->qkv, e->ctx, e->n_seq, e->T, H, e->stream);
+  if (mode == 2)
+    return launch_attention_fa(e->m_qkv3, e->m_ctx3, e->qkv, e->ctx, e->n_seq, e->T, H, e->stream, e->next_dir());
   AttnParams p{e->qkv, e->ctx, e->T, 3 * d, d, d, 2 * d, 1, 0, 1, e->T};
   return launch_attention(p, e->n_seq, H, hd, e->stream);
 }
@@ -899,6 +908,7 @@ int pgibbs_create(const pgibbs_model_config* cfg, int32_t device_id, pgibbs_engi
   if (const char* f = getenv("PGIBBS_GEMM_SPLIT")) g_gemm_split = atoi(f);
   if (const char* f = getenv("PGIBBS_PDL")) g_pdl = atoi(f);
   if (const char* f = getenv("PGIBBS_GRAPH")) g_graph = atoi(f);
+  if (const char* f = getenv("PGIBBS_ZIGZAG")) g_zigzag = atoi(f);
   if (cfg->embed_dim % cfg->heads) return fail("embed_dim %% heads != 0");
   if (cfg->embed_dim % 64 || cfg->ffn_dim % 64) return fail("embed_dim and ffn_dim must be multiples of 64");
   if (cfg->embed_dim > kMaxVecPerLane * 128) return fail("embed_dim %d too large (max %d)", cfg->embed_dim, kMaxVecPerLane * 128);

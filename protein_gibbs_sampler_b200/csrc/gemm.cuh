@@ -43,6 +43,7 @@ struct GemmParams {
   int seq_len;          // token position t = row % seq_len
   const float2* rope;   // [seq_len, head_dim/2] (cos, sin)
   // EPI_RESID_F32 only: K-split of the partly-filled last wave (see gemm_work_unit).  split <= 1: off.
+  int reverse;          // walk the tiles from the last row block down (see pgibbs_engine::zigzag)
   int split;            // parts each last-wave tile is cut into along K
   int32_t* flags;       // [last-wave tile][part][CTA rank][epilogue warp]: 1 once that warp's reduce-adds have landed;
                         // zero between launches (the one waiter of a flag clears it), so a launch captured in a
@@ -314,7 +315,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t phase = 0;
     WorkUnit u;
     for (int it = 0; gemm_work_unit(it, group, num_groups, num_tiles, num_kb, split, u); ++it) {
-      const int m_blk = u.tile / n_tiles, n_blk = u.tile % n_tiles;
+      const int tile = p.reverse ? num_tiles - 1 - u.tile : u.tile;
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int a_row = (m_blk * CG + rank) * kBM, b_row = n_blk * BN + rank * kBNL;
       for (int kb = u.kb0; kb < u.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -390,7 +392,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int sbuf = 0;
     WorkUnit u;
     for (int it = 0; gemm_work_unit(it, group, num_groups, num_tiles, num_kb, split, u); ++it) {
-      const int m_blk = u.tile / n_tiles, n_blk = u.tile % n_tiles;
+      const int tile = p.reverse ? num_tiles - 1 - u.tile : u.tile;
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
       const int row0 = (m_blk * CG + rank) * kBM + quad * 32;

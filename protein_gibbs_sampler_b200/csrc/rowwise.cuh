@@ -173,6 +173,7 @@ struct LnParams {
   Schedule sched;
   int iter, T;
   int identity;    // copy the (gathered) rows without normalising (ESM-1 has no final LayerNorm)
+  int reverse;     // blocks take the rows from the last one down (see pgibbs_engine::zigzag)
 };
 
 // VPL = float4 vectors held per lane (>= ceil(d / 128)): sized to the model so that the row fits in few registers
@@ -185,9 +186,10 @@ __global__ void __launch_bounds__(256, VPL <= 10 ? 4 : 2) layernorm_kernel(LnPar
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warps_per_block = blockDim.x >> 5;
-  const int orow = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  int orow = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (orow >= p.rows_out) return;
+  if (p.reverse) orow = p.rows_out - 1 - orow;
   long long srow = orow;
   if (p.sched.positions) {
     const int chain = orow / p.sched.P, q = orow % p.sched.P;
