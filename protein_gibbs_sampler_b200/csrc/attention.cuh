@@ -69,6 +69,7 @@ struct AttnParams {
   int inner, inner_stride, row_step;
   long long outer_stride;
   int q_begin = 0;    // first query row handled by this launch (blockIdx.x counts tiles from here)
+  int reverse = 0;    // msa_col_attention_kernel: walk the columns from the last one down (pgibbs_engine::zigzag)
 };
 
 constexpr int kAttnBK = 64;   // keys per smem chunk

@@ -644,7 +644,7 @@ static int run_msa_row_attention(pgibbs_engine* e) {
   if (legacy < 0) { const char* v = getenv("PGIBBS_MSA_ROW"); legacy = (v && !strcmp(v, "legacy")) ? 1 : 0; }
   ProfScope ps(e, "msa_row_attention");
   if (hd == 64 && e->T <= 256 && !legacy) {
-    MsaRowParams p{e->R, e->T, c.heads, (e->T + 15) & ~15, 0};
+    MsaRowParams p{e->R, e->T, c.heads, (e->T + 15) & ~15, 0, e->next_dir()};
     p.stages = std::min(8, (227 * 1024 - 2 * kMrQBytes - 2048) / mr_stage_bytes(p.NK));
     const int smem = mr_smem_bytes(p.NK, p.stages);
     static int configured = 0;
@@ -724,6 +724,7 @@ static int forward(pgibbs_engine* e, const Schedule& sched_in, int n_chains, int
       {
         ProfScope ps(e, "msa_col_attention");
         AttnParams ap{e->qkv, e->ctx, e->R, 3 * d, d, d, 2 * d, e->T, 1, e->T, static_cast<long long>(e->R) * e->T};
+        ap.reverse = e->next_dir();   // (only the dedicated column kernel honours it)
         const char* m = hd == 64 ? launch_msa_col_attention(ap, e->B * e->T, c.heads, st) : "";
         if (m && *m) return fail("%s", m);
         if (m) TRY(launch_attention(ap, e->B * e->T, c.heads, hd, st));  // shape not covered: generic kernel

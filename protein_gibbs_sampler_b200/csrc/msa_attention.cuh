@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(64 * HG) msa_col_attention_kernel(AttnParams p
   __half* sQ = reinterpret_cast<__half*>(col_smem);  // [HG][32 * LDS]
   __half* sK = sQ + HG * 32 * LDS;
   __half* sV = sK + HG * 32 * LDS;
-  const int s = blockIdx.x, head0 = blockIdx.y * HG;
+  const int s = p.reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x, head0 = blockIdx.y * HG;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
   const long long row0 = (s / p.inner) * p.outer_stride + static_cast<long long>(s % p.inner) * p.inner_stride;
   const long long rs = static_cast<long long>(p.row_step) * p.ld;

@@ -26,6 +26,7 @@ struct MsaRowParams {
   int R, C, H;   // alignment depth, columns (tokens per row), heads
   int NK;        // C rounded up to a multiple of 16 (<= 256)
   int stages;    // ring depth
+  int reverse;   // walk the MSAs from the last one down (pgibbs_engine::zigzag)
 };
 
 constexpr int kMrThreads = 256;
@@ -53,7 +54,7 @@ msa_row_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = blockIdx.x * 128, head = blockIdx.y, b = blockIdx.z;
+  const int i0 = blockIdx.x * 128, head = blockIdx.y, b = p.reverse ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
   const int R = p.R, NK = p.NK, d = p.H * 64;
   const int kv_bytes = NK * 128;
 

@@ -36,6 +36,27 @@ def make(cfg, seed, rng="replay"):
 
 
 # ------------------------------------------------------------------------------------------- operators
+
+
+def test_gemm_last_wave_k_split_opt_in(monkeypatch):
+    """PGIBBS_GEMM_SPLIT=1 (off by default: DESIGN.md section 4): FC2's partly filled last wave cut along K, the parts'
+    reduce-adds ordered by flags.  Same value as the unsplit kernel up to the fp32 regrouping x + p0 + p1, and
+    bit-identical from run to run."""
+    from protein_gibbs_sampler_b200.engine import op_gemm
+    torch.manual_seed(0)
+    M, N, K = 16512, 1280, 5120          # 325 pair tiles on 74 pairs: 29 tiles in the last wave
+    A, B, bias, C0 = torch.randn(M, K) * 0.5, torch.randn(N, K) * 0.05, torch.randn(N), torch.randn(M, N)
+    monkeypatch.setenv("PGIBBS_GEMM_SPLIT", "0")
+    plain = op_gemm(A, B, bias, C=C0, epilogue=2)
+    monkeypatch.setenv("PGIBBS_GEMM_SPLIT", "1")
+    split1 = op_gemm(A, B, bias, C=C0, epilogue=2)
+    split2 = op_gemm(A, B, bias, C=C0, epilogue=2)
+    monkeypatch.setenv("PGIBBS_GEMM_SPLIT", "0")
+    op_gemm(A[:128], B, bias, C=C0[:128], epilogue=2)     # leaves the process-wide switch off again
+    assert torch.equal(split1, split2)
+    assert not torch.equal(split1, plain)                 # the split did happen ...
+    assert rel(split1, plain) < 1e-5                      # ... and only regroups an fp32 sum (operand rounding: 3e-4)
+
 @pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (300, 320, 320, 64), (516, 960, 320, 192),
                                       (1000, 1280, 1280, 256), (129, 336, 128, 128), (2050, 5120, 1280, 256)])
 def test_gemm_operator(M, N, K, bn):
