@@ -13,6 +13,23 @@ def spec_args(text):
     return value
 
 
+def spec_lines(input_h, echo_h, n_fields, what, complain=True):
+    """The runs of a specification file: non-empty lines split at tabs.  A line with the wrong number of fields is
+    reported (like the reference scripts do) and skipped; accepted lines are echoed to stdout and to `echo_h`."""
+    for raw in input_h:
+        fields = raw.strip().split("\t")
+        if fields == [""]:
+            continue
+        if len(fields) != n_fields:
+            if complain:
+                print(f"Expected {n_fields} values in specification file ({what}), got {len(fields)}")
+                print("\t".join(fields))
+            continue
+        print("\t".join(fields))
+        print("\t".join(fields), file=echo_h)
+        yield fields
+
+
 def add_weight_flags(parser):
     parser.add_argument("--checkpoint", default=None,
                         help="path to a fair-esm checkpoint (.pt) for --model.  Without it the model runs on seeded "

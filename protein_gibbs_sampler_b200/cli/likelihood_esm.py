@@ -53,25 +53,24 @@ def main(input_h, output_h, masking_off, sampler, batch_size, mask_distance, csv
 
 def build_parser():
     parser = argparse.ArgumentParser(
-        description=textwrap.dedent("""Calculates average log likelihood of a fasta ESM BERT model.
+        description=textwrap.dedent("""Pseudo-log-likelihood of every sequence of a fasta under an ESM masked language
+            model (B200 engine): mean over positions of log p(true residue | rest, position masked).
 
-            writes a tab separated output file with columns:
-            sequence name, score
+            Output: one line per sequence, name and score, tab (or comma) separated.
             """), formatter_class=RawAndDefaultsFormatter)
     parser.add_argument("-o", type=str, default=None, help="output table (default: stdout)")
-    parser.add_argument("-i", default=None, help="A fasta file with sequences to calculate log likelihood for. Any "
-                                                 "gaps or stop codons will be removed before scoring.")
-    parser.add_argument("--batch_size", type=int, default=1, help="How many sequences to batch together.")
+    parser.add_argument("-i", default=None, help="fasta to score (gaps and '*' are stripped first); default stdin")
+    parser.add_argument("--batch_size", type=int, default=1, help="sequences per call and masked copies per forward")
     parser.add_argument("--device", type=str, default="gpu", help="gpu (cuda:0) or cuda:[int]; the engine has no cpu path")
-    parser.add_argument("--masking_off", action="store_true", default=False, help="If set, no masking is done.")
+    parser.add_argument("--masking_off", action="store_true", default=False, help="score every position from ONE unmasked forward")
     parser.add_argument("--mask_distance", type=int, default=None,
-                        help="If set, then multiple positions will be masked at a time, with (mask_distance - 1) "
-                             "non-masked positions between each masked position. Default: mask positions one at a time.")
-    parser.add_argument("--model", type=str, default="esm1v", choices=sorted(model_map), help="Which model to use.")
-    parser.add_argument("--csv", action="store_true", default=False, help="If set, then output will be a csv file.")
-    parser.add_argument("--score_name", type=str, default=None, help="what to put as the second column name.")
+                        help="mask every mask_distance-th position of a copy at once (mask_distance copies per sequence instead "
+                             "of one per residue); default: one position per copy")
+    parser.add_argument("--model", type=str, default="esm1v", choices=sorted(model_map), help="model triple (architecture + alphabet)")
+    parser.add_argument("--csv", action="store_true", default=False, help="comma instead of tab separated")
+    parser.add_argument("--score_name", type=str, default=None, help="header of the score column (default: the model name)")
     parser.add_argument("--positionwise", type=str, default=None,
-                        help="If set, positionwise log likelihoods are written to this file: id and a ';' separated list.")
+                        help="also write per-position values here: name, then the ';'-joined list rounded to 3 decimals")
     add_weight_flags(parser)
     return parser
 

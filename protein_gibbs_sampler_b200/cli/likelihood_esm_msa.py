@@ -11,7 +11,6 @@ import subprocess
 import sys
 import tempfile
 import textwrap
-import warnings
 
 from tqdm import tqdm
 
@@ -21,7 +20,7 @@ from ..fasta import (RawAndDefaultsFormatter, SequenceSubsetter, parse_fasta, pa
                      write_sequential_fasta)
 from . import add_weight_flags, build_model
 from .likelihood_esm import write_scores
-from .pgen_msa_revised import delete_msa_cols, generate_alignment, run_phmmer
+from .pgen_msa_revised import ReferenceDb, delete_msa_cols
 
 model_map = {"esm_msa1": models.ESM_MSA1}
 
@@ -45,7 +44,7 @@ def add_to_msa(msa, new_seq):
 
 
 class ContextBuilder:
-    """Query name -> alignment with the query on top (the reference's `get_in_msa` closure, :77-107)."""
+    """Query name -> alignment with the query on top (what the reference's `get_in_msa` closure returns, :77-107)."""
 
     def __init__(self, in_seqs, in_msas=None, reference_msa=None, subset_strategy="random", alignment_size=sys.maxsize,
                  subset_random_seed=None, redraw=False, unaligned_queries=False, keep_identical=False):
@@ -53,16 +52,18 @@ class ContextBuilder:
         self.reference_msa = reference_msa
         self.strategy, self.size, self.seed = subset_strategy, alignment_size, subset_random_seed
         self.redraw, self.unaligned_queries, self.keep_identical = redraw, unaligned_queries, keep_identical
-        self.fixed = self.db_path = self.db = None
+        self.fixed = self.db = None
         if in_msas:
             return
-        if subset_strategy == "top_hits":   # phmmer database: the reference sequences under sequential names
-            with tempfile.NamedTemporaryFile(delete=False, mode="w") as tmp:
-                write_sequential_fasta(tmp, reference_msa)
-            self.db_path = tmp.name
-            self.db = dict(zip(*parse_fasta(self.db_path, return_names=True)))
+        if subset_strategy == "top_hits":
+            self.db = ReferenceDb(reference_msa)
         else:
             self.fixed = self.draw()
+
+    def close(self):
+        if self.db is not None:
+            self.db.__exit__()
+            self.db = None
 
     def draw(self):
         return SequenceSubsetter.subset(self.reference_msa, self.size, strategy=self.strategy, random_seed=self.seed)
@@ -71,16 +72,8 @@ class ContextBuilder:
         if self.in_msas:
             return self.in_msas[name]
         seq = self.in_seqs[name]
-        if self.strategy == "top_hits":
-            rows = [seq]
-            for hit in run_phmmer(seq, self.db_path):
-                if len(rows) == self.size:
-                    break
-                if self.db[hit] != seq or self.keep_identical:
-                    rows.append(self.db[hit])
-            if len(rows) < self.size:
-                warnings.warn(f"Warning: fewer than {self.size - 1} hits found for template seq {name}")
-            return generate_alignment({"1": rows})[1]
+        if self.db is not None:
+            return self.db.alignment_with_top_hits(name, seq, self.size, self.keep_identical)
         context = self.fixed
         if self.redraw:
             context = self.draw()
@@ -118,50 +111,44 @@ def main(input_h, output_h, masking_off, sampler, reference_msa_handle=None, in_
     finally:
         if positionwise_h is not None:
             positionwise_h.close()
-        if context_of.db_path:
-            os.unlink(context_of.db_path)
+        context_of.close()
 
 
 def build_parser():
     parser = argparse.ArgumentParser(
-        description=textwrap.dedent("""Calculates average log likelihood of a fasta from the ESM-MSA model.
+        description=textwrap.dedent("""Pseudo-log-likelihood of every query sequence under the MSA Transformer (B200
+            engine), each query scored as the top row of a context alignment built from --reference_msa.
 
-            writes a tab separated output file with columns:
-            sequence name, score
+            Output: one line per query, name and score, tab (or comma) separated.
             """), formatter_class=RawAndDefaultsFormatter)
     parser.add_argument("-o", type=str, default=None, help="output table (default: stdout)")
-    parser.add_argument("-i", default=None, help="A fasta file with sequences to calculate log likelihood for")
+    parser.add_argument("-i", default=None, help="fasta of the queries; default stdin")
     parser.add_argument("--reference_msa", default=None, required=True,
-                        help="A fasta file with an msa to use as a reference. If subset_strategy is top_hits, then "
-                             "this should be an unaligned fasta of reference sequences.")
+                        help="context alignment (fasta / a2m); with --subset_strategy top_hits an UNALIGNED fasta that is "
+                             "searched per query")
     parser.add_argument("--device", type=str, default="gpu", help="gpu (cuda:0) or cuda:[int]; the engine has no cpu path")
-    parser.add_argument("--masking_off", action="store_true", default=False, help="If set, no masking is done.")
+    parser.add_argument("--masking_off", action="store_true", default=False, help="score every position from ONE unmasked forward")
     parser.add_argument("--delete_insertions", action="store_true", default=False,
-                        help="If set, then remove all lowercase and '.' characters from input sequences. Default: "
-                             "convert lower to upper and '.' to '-'.")
+                        help="drop a2m insertion columns (lower case, '.') instead of upper-casing them / turning '.' into '-'")
     parser.add_argument("--alignment_size", type=int, default=sys.maxsize,
-                        help="Use this many sequences from the reference alignment, recommended values are 31-255. "
-                             "Default: the entire reference alignment.")
+                        help="context rows taken from the reference (31-255 is sensible); default: all of them")
     parser.add_argument("--keep_identical", action="store_true", default=False,
-                        help="For subset_strategy=top_hits, keep reference sequences identical to the query.")
-    parser.add_argument("--batch_size", type=int, default=1, help="Batch size (masked msa copies per forward).")
+                        help="top_hits: keep hits identical to the query")
+    parser.add_argument("--batch_size", type=int, default=1, help="queries per call and masked MSA copies per forward")
     parser.add_argument("--subset_strategy", default="random", choices=["in_order", "random", "top_hits"],
-                        help="random: draw randomly, in_order: take the sequences listed first in the reference "
-                             "alignment, top_hits: run phmmer for each query against the reference sequences and use "
-                             "a MAFFT MSA of the top hits as the reference.")
+                        help="random: a shuffle's first rows; in_order: the first rows; top_hits: phmmer the query against "
+                             "the references and mafft-align it with its best hits")
     parser.add_argument("--subset_random_seed", default=None, type=int,
-                        help="Seed of the random subsetter; incremented by 1000000 after each draw.")
+                        help="seed of the random subset (+1000000 after every draw)")
     parser.add_argument("--redraw", action="store_true", default=False,
-                        help="With subset_strategy random: a new random draw of reference sequences for each query.")
+                        help="random: draw a fresh subset for every query instead of one for all")
     parser.add_argument("--unaligned_queries", action="store_true", default=False,
-                        help="The queries are unaligned (or from another alignment): use muscle -profile to add each "
-                             "one to the reference alignment.")
+                        help="queries are not in the reference's column frame: add each one with muscle -profile")
     parser.add_argument("--mask_distance", type=int, default=None,
-                        help="If set, then multiple positions will be masked at a time, with (mask_distance - 1) "
-                             "non-masked positions between each masked position. Default: mask positions one at a time.")
-    parser.add_argument("--csv", action="store_true", default=False, help="If set, then outputs will be csv files.")
+                        help="mask every mask_distance-th position of a copy at once; default: one position per copy")
+    parser.add_argument("--csv", action="store_true", default=False, help="comma instead of tab separated")
     parser.add_argument("--positionwise", type=str, default=None,
-                        help="If set, positionwise log likelihoods are written to this file: id and a ';' separated list.")
+                        help="also write per-position values here: name, then the ';'-joined list rounded to 3 decimals")
     add_weight_flags(parser)
     return parser
 

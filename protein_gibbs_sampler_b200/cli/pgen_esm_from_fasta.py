@@ -13,7 +13,7 @@ from pathlib import Path
 from .. import models
 from ..esm_sampler import ESM_sampler
 from ..fasta import RawAndDefaultsFormatter, add_gaps_back, parse_fasta, unalign, write_sequential_fasta
-from . import add_weight_flags, build_model, spec_args
+from . import add_weight_flags, build_model, spec_args, spec_lines
 from .pgen_esm import EPILOG
 
 model_map = {"esm1b": models.ESM1b, "esm6": models.ESM6, "esm12": models.ESM12, "esm34": models.ESM34,
@@ -41,42 +41,32 @@ def sample_from_seeds(sampler, seeds, n_outputs, line_args, keep_gap_positions=F
 def main(input_h, output_p, args, sampler=None):
     if sampler is None:
         sampler = ESM_sampler(build_model(model_map, args), device=args.device)
-    with open(output_p / "specification.tsv", "w") as output_h:
-        for line in input_h:
-            line = line.strip()
-            if not line:
-                continue
-            fields = line.split("\t")
-            if len(fields) != 3:   # the reference skips such lines silently (:22)
-                continue
-            print("\t".join(fields))
-            print("\t".join(fields), file=output_h)
-            seeds = parse_fasta(fields[2], clean=None)
-            sequences = sample_from_seeds(sampler, seeds, args.num_output_sequences, spec_args(fields[1]),
-                                          args.keep_gap_positions)
-            write_sequential_fasta(output_p / (fields[0] + ".fasta"), sequences)
+    with open(output_p / "specification.tsv", "w") as echo_h:
+        # (the reference skips malformed lines silently here, :22)
+        for name, arg_text, seeds_path in spec_lines(input_h, echo_h, 3, "name, line_args, seed fasta", complain=False):
+            sequences = sample_from_seeds(sampler, parse_fasta(seeds_path, clean=None), args.num_output_sequences,
+                                          spec_args(arg_text), args.keep_gap_positions)
+            write_sequential_fasta(output_p / (name + ".fasta"), sequences)
 
 
 def build_parser():
     parser = argparse.ArgumentParser(
-        description=textwrap.dedent("""Samples from an ESM BERT model to generate new protein sequences.
+        description=textwrap.dedent("""Gibbs-sample new protein sequences, each started from a randomly chosen sequence of
+            a seed fasta (B200 engine).
 
-            Input should be a tab separated file where columns are:
-            sample name, dict of sampler arguments, fasta of seed sequences
+            One run per input line:  <run name> TAB <python dict of sampler arguments> TAB <seed fasta>
             """),
         epilog=EPILOG.replace("seed_seq: protein sequence (or list of sequences) to start from\n", ""),
         formatter_class=RawAndDefaultsFormatter)
-    parser.add_argument("-o", default=".", help="a directory to save the outputs to.")
-    parser.add_argument("-i", default=None, help="tab separated file where the columns are as follows: [sample name] "
-                                                 "\\t [dict of arguments for the sampler] \\t [path to fasta file].")
+    parser.add_argument("-o", default=".", help="output directory (created if missing)")
+    parser.add_argument("-i", default=None, help="specification file (name TAB dict TAB seed fasta per line); default stdin")
     parser.add_argument("--batch_size", type=int, default=1, choices=[1],
                         help="kept for compatibility (must be 1): chains of equal length are batched on the device anyway.")
-    parser.add_argument("--num_output_sequences", type=int, default=1, help="total number of sequences to generate.")
+    parser.add_argument("--num_output_sequences", type=int, default=1, help="sequences written per run")
     parser.add_argument("--device", type=str, default="gpu", help="gpu (cuda:0) or cuda:[int]; the engine has no cpu path")
-    parser.add_argument("--model", type=str, default="esm1b", choices=sorted(model_map), help="which model to use")
+    parser.add_argument("--model", type=str, default="esm1b", choices=sorted(model_map), help="model triple (architecture + alphabet)")
     parser.add_argument("--keep_gap_positions", action="store_true", default=False,
-                        help="If set, remember where the gaps are in the seed and add them back into the same "
-                             "positions of the generated sequence.")
+                        help="put the seed's gap characters back at their columns in the generated sequence")
     add_weight_flags(parser)
     return parser
 

@@ -71,48 +71,65 @@ def generate_alignment(sequences, ep=0.0, op=1.53):
     return parse_fasta_string(out.stdout.decode("utf-8"), True)
 
 
+class ReferenceDb:
+    """The reference sequences as a phmmer database: a temporary fasta with the records renamed 0..n-1 (the names
+    phmmer reports), removed again on exit."""
+
+    def __init__(self, sequences):
+        self.by_name = {str(i): s for i, s in enumerate(sequences)}
+        with tempfile.NamedTemporaryFile(delete=False, mode="w") as fh:
+            write_sequential_fasta(fh, sequences)
+        self.path = fh.name
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        os.unlink(self.path)
+
+    def alignment_with_top_hits(self, name, query, size, keep_identical, ep=0.0, op=1.53, max_mode=False):
+        """mafft alignment of `query` (row 0: mafft keeps the input order) with its best phmmer hits, `size` rows at
+        most; hits equal to the query are skipped unless keep_identical."""
+        rows = [query]
+        for hit in run_phmmer(query, self.path, max_mode=max_mode):
+            if len(rows) == size:
+                break
+            if keep_identical or self.by_name[hit] != query:
+                rows.append(self.by_name[hit])
+        if len(rows) < size:
+            warnings.warn(f"Warning: fewer than {size - 1} hits found for template seq {name}")
+        return generate_alignment({"1": rows}, ep=ep, op=op)[1]
+
+
+def design_frame(alignment, legacy, gap_percent_threshold):
+    """(alignment to sample on, row to resample, 0-based columns to leave alone).  Default: the template stays row 0,
+    its gap columns are removed and mostly-gap columns are excluded.  Legacy: the template is swapped to the LAST row
+    and every column may change."""
+    if legacy:
+        return [alignment[-1]] + alignment[1:-1] + [alignment[0]] if len(alignment) > 1 else list(alignment), -1, []
+    trimmed = delete_msa_cols(alignment, [i for i, c in enumerate(alignment[0]) if c == "-"])
+    return trimmed, 0, apply_gap_threshold(trimmed, gap_percent_threshold)
+
+
 def pgen_msa(templates_path, references_path, output_path, seqs_per_template, keep_identical, steps, passes, burn_in,
              device, model, alignment_size, ep, op, top_k, legacy=False, gap_percent_threshold=80, debug=False,
              sampler=None):
-    template_seqs = list(zip(*parse_fasta(templates_path, clean="unalign", return_names=True)))
-    reference_list = parse_fasta(references_path, clean="unalign")
+    names, templates = parse_fasta(templates_path, clean="unalign", return_names=True)
     gibbs_sampler = sampler if sampler is not None else ESM_MSA_sampler(model_map[model](), device=device)
-
-    tmp_file = tempfile.NamedTemporaryFile(delete=False, mode="w")
-    write_sequential_fasta(tmp_file, reference_list)   # phmmer database: references renamed 0..n-1
-    tmp_file.close()
-    reference_db_path = tmp_file.name
-    reference_seqs = {str(i): s for i, s in enumerate(reference_list)}
-    try:
-        with tqdm(total=len(template_seqs) * seqs_per_template) as pbar, open(output_path, "w") as outfile:
-            for template_name, template_seq in template_seqs:
-                unaligned = [template_seq]
-                for hit in run_phmmer(template_seq, reference_db_path, max_mode=debug):
-                    if len(unaligned) == alignment_size:
-                        break
-                    if reference_seqs[hit] != template_seq or keep_identical:
-                        unaligned.append(reference_seqs[hit])
-                if len(unaligned) < alignment_size:
-                    warnings.warn(f"Warning: fewer than {alignment_size - 1} hits found for template seq {template_name}")
-                _, alignment = generate_alignment({"1": unaligned}, ep=ep, op=op)   # mafft keeps the input order
-                exclude_positions = []
-                if not legacy:   # template is row 0: drop its gap columns, skip mostly-gap columns
-                    gaps = [i for i, c in enumerate(alignment[0]) if c == "-"]
-                    alignment = delete_msa_cols(alignment, gaps)
-                    exclude_positions = apply_gap_threshold(alignment, gap_percent_threshold)
-                else:            # original behaviour: the template is the LAST row
-                    alignment[0], alignment[-1] = alignment[-1], alignment[0]
-                # all seqs_per_template chains of this template as one device batch (the reference runs them one by
-                # one, a batch-1 forward per step: pgen_msa_revised.py:107-115); same RNG consumption order
-                new_seqs = gibbs_sampler.generate_single_batch(alignment, seqs_per_template, steps=steps, passes=passes,
-                                                               burn_in=burn_in, k=top_k,
-                                                               target_index=-1 if legacy else 0,
-                                                               exclude_positions=exclude_positions)
-                for i, new_seq in enumerate(new_seqs):
-                    print(f">{i}_{template_name}\n{new_seq.replace('-', '')}", file=outfile, flush=True)
-                    pbar.update(1)
-    finally:
-        os.unlink(reference_db_path)
+    with ReferenceDb(parse_fasta(references_path, clean="unalign")) as db, open(output_path, "w") as outfile, \
+            tqdm(total=len(templates) * seqs_per_template) as pbar:
+        for name, template in zip(names, templates):
+            alignment = db.alignment_with_top_hits(name, template, alignment_size, keep_identical, ep, op, debug)
+            alignment, target, frozen = design_frame(alignment, legacy, gap_percent_threshold)
+            # all seqs_per_template chains of this template as ONE device batch (the reference runs them one by one,
+            # a batch-1 forward per step: pgen_msa_revised.py:107-115); the RNG is consumed in the same order
+            designs = gibbs_sampler.generate_single_batch(alignment, seqs_per_template, steps=steps, passes=passes,
+                                                          burn_in=burn_in, k=top_k, target_index=target,
+                                                          exclude_positions=frozen)
+            for k, design in enumerate(designs):
+                outfile.write(">%d_%s\n%s\n" % (k, name, design.replace("-", "")))
+                outfile.flush()
+                pbar.update(1)
 
 
 def build_parser():
@@ -120,36 +137,34 @@ def build_parser():
         description=textwrap.dedent("""Samples from the ESM-MSA model to generate new protein sequences."""),
         formatter_class=RawAndDefaultsFormatter)
     parser.add_argument("--templates", default=None, required=True,
-                        help="an unaligned fasta file with sequences to mask for generating new sequences.")
+                        help="fasta of the (unaligned) sequences to re-design, one after the other")
     parser.add_argument("--references", default=None, required=True,
-                        help="an unaligned fasta file with reference sequences to search for homologs to the templates.")
-    parser.add_argument("-o", default=None, required=True, help="a fasta file to write generated sequences to")
+                        help="fasta of (unaligned) sequences searched with phmmer for homologs of each template")
+    parser.add_argument("-o", default=None, required=True, help="output fasta; records are named <k>_<template name>")
     parser.add_argument("--seqs_per_template", type=int, default=1,
-                        help="Number of new sequences to generate for each template sequence.")
+                        help="designs produced per template (run as one device batch)")
     parser.add_argument("--keep_identical", action="store_true", default=False,
-                        help="By default, if a template sequence is identical to the query sequence, it is thrown out. "
-                             "Set this if, for some reason you want to keep those.")
-    parser.add_argument("--steps", type=int, default=10, help="Randomly assign the input positions to this many mask "
-                        "bins, and mask and generate over one bin at a time.")
-    parser.add_argument("--passes", type=int, default=3, help="how many passes over the entire template sequence to make.")
-    parser.add_argument("--burn_in", type=int, default=1, help="A number of passes equal to burn_in will sample from the "
-                        "entire distribution, after which amino acids will be sampled from the top_k most likely.")
-    parser.add_argument("--top_k", type=int, default=1, help="Sample from the this many of the most probable amino "
-                        "acids, after burn in. If 0 then always sample from full distribution.")
+                        help="keep phmmer hits that are identical to the template (dropped otherwise)")
+    parser.add_argument("--steps", type=int, default=10, help="each pass shuffles the positions into this many "
+                        "bins; one bin is masked and resampled per forward")
+    parser.add_argument("--passes", type=int, default=3, help="number of sweeps over all positions")
+    parser.add_argument("--burn_in", type=int, default=1, help="sweeps that sample from the full "
+                        "distribution before --top_k takes effect")
+    parser.add_argument("--top_k", type=int, default=1, help="after burn-in draw only among the k likeliest "
+                        "residues (0: never restrict)")
     parser.add_argument("--legacy", action="store_true", default=False,
-                        help="Use the original implementation's behavior of sampling from the last sequence in the MSA "
-                             "rather than the first, and ignoring gap_percent_threshold.")
+                        help="first version's behaviour: the template goes LAST in the alignment and is resampled there; "
+                             "--gap_percent_threshold is not applied")
     parser.add_argument("--gap_percent_threshold", type=float, default=80.0,
-                        help="Don't resample positions where more than this percent of sequences in the alignment "
-                             "contain gaps. Ignored in legacy mode.")
-    parser.add_argument("--ep", type=float, default=0.0, help="ep parameter passed to MAFFT for alignments")
-    parser.add_argument("--op", type=float, default=1.53, help="op parameter passed to MAFFT for alignments")
+                        help="columns with more than this percentage of gaps are left as they are (not in --legacy mode)")
+    parser.add_argument("--ep", type=float, default=0.0, help="mafft --ep (offset / gap extension)")
+    parser.add_argument("--op", type=float, default=1.53, help="mafft --op (gap opening)")
     parser.add_argument("--device", type=str, default="gpu", help="gpu (cuda:0) or cuda:[int]; the engine has no cpu path")
-    parser.add_argument("--model", type=str, default="esm_msa1", choices=sorted(model_map), help="which model to use")
-    parser.add_argument("--alignment_size", type=int, default=32, help="how many sequences (template plus references) "
-                        "should be in the alignments used for sequence generation.")
-    parser.add_argument("--debug", action="store_true", default=False, help="run in debug mode. Runs phmmer in --max "
-                        "mode, to turn off pre-filters and allow finding very short hits.")
+    parser.add_argument("--model", type=str, default="esm_msa1", choices=sorted(model_map), help="model triple (architecture + alphabet)")
+    parser.add_argument("--alignment_size", type=int, default=32, help="rows of each working alignment: the template "
+                        "plus its best hits")
+    parser.add_argument("--debug", action="store_true", default=False, help="phmmer --max (no pre-filters: finds "
+                        "hits of very short sequences too)")
     add_weight_flags(parser)
     return parser
 
