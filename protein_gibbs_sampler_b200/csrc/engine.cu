@@ -787,9 +787,9 @@ static int forward(pgibbs_engine* e, const Schedule& sched_in, int n_chains, int
       CK(cudaFuncSetAttribute(head_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
     }
-    const int grid = std::min(g_num_sms, (rows + 7) / 8);
+    const int grid = std::min(g_num_sms, (rows + 11) / 12);
     ProfScope ps(e, "head_sample");
-    CK(launch_pdl(head_sample_kernel, dim3(grid), dim3(256), p.emb_in_smem ? emb_bytes : 0, st, p));
+    CK(launch_pdl(head_sample_kernel, dim3(grid), dim3(384), p.emb_in_smem ? emb_bytes : 0, st, p));
   }
   return 0;
 }

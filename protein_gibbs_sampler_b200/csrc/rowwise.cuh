@@ -407,7 +407,7 @@ struct HeadParams {
   float* logp_out;           // [rows] log_softmax(logits)[target] over the whole vocabulary
 };
 
-__global__ void __launch_bounds__(256) head_sample_kernel(HeadParams p) {
+__global__ void __launch_bounds__(384) head_sample_kernel(HeadParams p) {
   extern __shared__ float s_emb[];
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
@@ -459,22 +459,39 @@ __global__ void __launch_bounds__(256) head_sample_kernel(HeadParams p) {
         v[k] = a;
       }
     }
-    // vocabulary projection: lane v ends up holding logit v (v < 32); logit 32.. kept in `extra` on lane v-32
+    // vocabulary projection: lane v ends up holding logit v (v < 32); logit 32.. kept in `extra` on lane v-32.
+    // Four tokens at a time: their dot products and the four butterfly reductions are independent chains, which is
+    // what hides the shared-memory and shuffle latency with only 12 warps per SM (per-token arithmetic unchanged).
     float mine = 0.f, extra = 0.f;
-    for (int tok = 0; tok < p.V; ++tok) {
-      const float4* e = reinterpret_cast<const float4*>(E + static_cast<long long>(tok) * p.d);
-      float acc = 0.f;
+    for (int tok0 = 0; tok0 < p.V; tok0 += 4) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int k = 0; k < kMaxVecPerLane; ++k) {
-        const int i = lane + k * 32;
-        if (i < nvec) {
-          const float4 w = e[i];
-          acc = fmaf(v[k].x, w.x, acc); acc = fmaf(v[k].y, w.y, acc);
-          acc = fmaf(v[k].z, w.z, acc); acc = fmaf(v[k].w, w.w, acc);
+      for (int u = 0; u < 4; ++u) {
+        const int tok = tok0 + u < p.V ? tok0 + u : p.V - 1;   // clamp: the surplus lanes of the last group are ignored
+        const float4* e = reinterpret_cast<const float4*>(E + static_cast<long long>(tok) * p.d);
+#pragma unroll
+        for (int k = 0; k < kMaxVecPerLane; ++k) {
+          const int i = lane + k * 32;
+          if (i < nvec) {
+            const float4 w = e[i];
+            acc[u] = fmaf(v[k].x, w.x, acc[u]); acc[u] = fmaf(v[k].y, w.y, acc[u]);
+            acc[u] = fmaf(v[k].z, w.z, acc[u]); acc[u] = fmaf(v[k].w, w.w, acc[u]);
+          }
         }
       }
-      acc = warp_sum(acc) + __ldg(p.out_bias + tok);
-      if ((tok & 31) == lane) { if (tok < 32) mine = acc; else extra = acc; }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int tok = tok0 + u;
+        if (tok < p.V) {
+          const float a = acc[u] + __ldg(p.out_bias + tok);
+          if ((tok & 31) == lane) { if (tok < 32) mine = a; else extra = a; }
+        }
+      }
     }
     if (p.logits_out) {
       float* lo = p.logits_out + static_cast<long long>(row) * p.V;
