@@ -184,3 +184,75 @@ def test_sharded_generate_on_engine_equals_single_gpu(rng, gpu_lib):
         got = _run(make, kw, 12, (rank, 2, _own_slice_gather(rank, 2, 6)))
         lo, hi = parallel.shard_range(6, 2, rank)
         assert got[lo:hi] == want[lo:hi], (rng, rank)
+
+
+def test_generate_many_folds_one_chain_calls_in_rng_order():
+    """pgen_esm_from_fasta's loop (reference :27-33) folded into device batches: the seed choice, the position
+    schedule and the replay noise of every one-chain call are drawn in the loop's order, the chains run grouped by
+    sequence length -- same output as the call-by-call loop (stand-in engine keyed by the noise it is handed)."""
+    from protein_gibbs_sampler_b200.fasta import unalign
+    seeds = ["MKTAYIAKQR-ISFVK", "MKT.AYLAKQRQISFVKSH", "mrtayiakqrq-sfvk", "MKTAYIAKQRQISFVKSHFSRQ"]
+    for kw in (dict(num_iters=4, num_positions=3, burnin=2, top_k=2), dict(num_iters=3, in_order=True, num_positions=2),
+               dict(num_iters=2, num_positions_percent=50, leader_length=2), dict(num_iters=0), dict(num_iters=3)):
+        s = ESM_sampler(FakeModel(), device="cpu", rng="replay")
+        random.seed(9); torch.manual_seed(9)
+        folded = s.generate_many((unalign(random.choice(seeds))[0] for _ in range(9)), max_batch=4, **kw)
+        random.seed(9); torch.manual_seed(9)
+        looped = [s.generate(1, unalign(random.choice(seeds))[0], batch_size=1, show_progress_bar=False, **kw)[0]
+                  for _ in range(9)]
+        assert folded == looped, kw
+    with pytest.raises(ValueError, match="expecting str"):
+        s.generate_many([["MKT"]])
+
+
+class ScoringEngine(FakeEngine):
+    """`Engine.score` stand-in: log p of slot (chain, j) = -(position + target / 100), or 0 for a padding slot; also
+    checks what the device path relies on -- unmasked tokens resident, targets = the true tokens at the positions."""
+
+    def score(self, targets, mask=True, row=-1):
+        pos, n_iters, P, istr, cstr = self.sched
+        t = np.asarray(targets).reshape(-1, P)
+        rows = self.tok.shape[1]
+        out = np.zeros(t.shape, dtype=np.float32)
+        for c in range(t.shape[0]):
+            for j in range(P):
+                p_ = int(pos[c * cstr + j])
+                seq = self.tok[c, row if row >= 0 else 0] if rows > 1 or row < 0 else self.tok[c, 0]
+                if t[c, j] >= 0:
+                    assert int(seq[p_]) == int(t[c, j])
+                    out[c, j] = -(p_ + t[c, j] / 100.0)
+        self.calls = getattr(self, "calls", 0) + 1
+        return torch.from_numpy(out)
+
+
+@pytest.mark.parametrize("L,mask_distance,batch_size,with_masking", [(11, float("inf"), None, True), (11, 4, 2, True),
+                                                                    (11, 4, None, True), (7, 3, 1, True),
+                                                                    (9, float("inf"), None, False)])
+def test_device_scoring_host_mapping(L, mask_distance, batch_size, with_masking):
+    """log_likelihood_batch on the engine path: schedule / targets handed to `score`, and the way its [copies, P]
+    result is put back into the reference's copy-major output order (esm_sampler.py:331-352)."""
+    m = FakeModel()
+    m.model.engine = ScoringEngine()
+    s = ESM_sampler(m, device="cpu")
+    seq = (SEED_SEQ * 2)[:L]
+    toks = m.batch_converter([("0", seq)])[2][0].tolist()
+    mean, each = next(s.log_likelihood_batch([seq], with_masking=with_masking, mask_distance=mask_distance,
+                                             batch_size=batch_size))
+    n = int(min(mask_distance, L)) if with_masking else 1
+    order = [p for i in range(n) for p in range(i, L, n)]
+    assert each == pytest.approx([-((1 + p) + toks[1 + p] / 100.0) for p in order], abs=1e-5)
+    assert mean == pytest.approx(sum(each) / L, abs=1e-4)
+    # batch_size=None means len(seq_list) masked copies per forward, as in the reference (esm_sampler.py:305-306)
+    assert m.model.engine.calls == -(-n // (batch_size or 1))
+
+
+def test_device_scoring_host_mapping_msa():
+    m = FakeModel(msa=True)
+    m.model.engine = ScoringEngine()
+    s = ESM_MSA_sampler(m, device="cpu")
+    toks = m.batch_converter([[(str(i), q) for i, q in enumerate(MSA)]])[2][0]
+    for target, count_gaps in ((0, False), (1, False), (2, True)):
+        mean, each = s.log_likelihood(MSA, target_index=target, mask_distance=3, count_gaps=count_gaps)
+        L = len(MSA[0])
+        order = [p for i in range(3) for p in range(i, L, 3) if count_gaps or MSA[target][p] != "-"]
+        assert each == pytest.approx([-((1 + p) + int(toks[target, 1 + p]) / 100.0) for p in order], abs=1e-5)
