@@ -244,6 +244,39 @@ def test_likelihood_esm_msa_cli_contexts(tmp_path):
     assert b.seed == 2000005
 
 
+def test_reference_db_top_hits_and_design_frame(monkeypatch):
+    """Host logic shared by pgen_msa_revised and likelihood_esm_msa --subset_strategy top_hits (phmmer / mafft stubbed:
+    hits in database order, sequences right-padded with gaps): hit selection, the size cap, identical-hit filtering,
+    the too-few-hits warning, clean-up of the temporary database; and the two template frames of pgen_msa_revised."""
+    from protein_gibbs_sampler_b200.cli import pgen_msa_revised as cli
+    seen = {}
+
+    def fake_phmmer(query, db, max_mode=False):
+        seen["db"] = db
+        assert fasta.parse_fasta(db) == refs           # the database holds the references, renamed 0..n-1
+        return fasta.parse_fasta(db, return_names=True)[0]
+
+    def fake_mafft(groups, ep=0.0, op=1.53):
+        rows = groups["1"]
+        width = max(len(r) for r in rows)
+        return ["1_%d" % i for i in range(len(rows))], [r + "-" * (width - len(r)) for r in rows]
+    monkeypatch.setattr(cli, "run_phmmer", fake_phmmer)
+    monkeypatch.setattr(cli, "generate_alignment", fake_mafft)
+    refs = ["MAGIK", "MEADAL", "MAGIC", "MEADQLK"]
+    with cli.ReferenceDb(refs) as db:
+        assert db.alignment_with_top_hits("t", "MAGIC", 3, keep_identical=False) == ["MAGIC-", "MAGIK-", "MEADAL"]
+        assert db.alignment_with_top_hits("t", "MAGIC", 4, keep_identical=True) == \
+            ["MAGIC-", "MAGIK-", "MEADAL", "MAGIC-"]
+        with pytest.warns(UserWarning, match="fewer than 5 hits"):
+            assert len(db.alignment_with_top_hits("t", "MAGIC", 6, keep_identical=False)) == 4
+        assert os.path.exists(seen["db"])
+    assert not os.path.exists(seen["db"])
+    msa = ["MA-GIC", "MAAG-C", "-AAGIC"]
+    assert cli.design_frame(msa, legacy=False, gap_percent_threshold=30) == (["MAGIC", "MAG-C", "-AGIC"], 0, [0, 3])
+    assert cli.design_frame(msa, legacy=True, gap_percent_threshold=30) == (["-AAGIC", "MAAG-C", "MA-GIC"], -1, [])
+    assert cli.design_frame(msa[:1], legacy=True, gap_percent_threshold=30) == (["MA-GIC"], -1, [])
+
+
 # ------------------------------------------------------------------------------------------------ GPU: end to end
 AA = set("ACDEFGHIKLMNPQRSTVWY")
 
