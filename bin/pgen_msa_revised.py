@@ -3,4 +3,4 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from protein_gibbs_sampler_b200.cli import pgen_msa_revised as _m
-_m.main(sys.argv[1:]) if "pgen_msa_revised" == "pgen_msa_revised" else _m.cli()
+_m.main(sys.argv[1:])

@@ -75,7 +75,7 @@ int pgibbs_set_chain_offset(pgibbs_engine* e, int64_t first_chain);
  * [first_iter, first_iter + num_iters): <mask> scatter (if mask_flag) -> forward -> generate_step at every
  * scheduled position -> write-back, entirely on device, no host synchronisation between iterations.
  * burnin: iterations with index < burnin sample the full candidate set (generate_step `sample=True`);
- * top_k <= 0 or > n_valid also means the full set.  temperature <= 0 means None.  Asynchronous. */
+ * top_k <= 0 or > n_valid also means the full set.  temperature = NaN means None; any other value divides the logits (esm_sampler.py:24-25: a negative one inverts the ranking; 0 is rejected).  Asynchronous. */
 int pgibbs_run(pgibbs_engine* e, int32_t first_iter, int32_t num_iters, int64_t burnin, int32_t top_k,
                float temperature, int32_t mask_flag, const int32_t* valid_ids, int32_t n_valid);
 /* ESM_MSA_sampler.generate_single's step (esm_msa_sampler.py:132-145): mask `mask_row` of every MSA at the

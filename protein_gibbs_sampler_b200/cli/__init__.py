@@ -4,10 +4,37 @@ import sys
 
 
 def spec_args(text):
-    """The dict literal of a specification line (`/root/reference/src/pgen/pgen_esm.py:25` uses bare `eval`).
-    Evaluated without builtins; `float('inf')` / `inf` -- the documented `burnin` values -- stay available."""
-    value = eval(text, {"__builtins__": {}}, {"float": float, "int": int, "inf": float("inf"), "range": range,
-                                               "list": list})
+    """The dict literal of a specification line.  `/root/reference/src/pgen/pgen_esm.py:25` uses bare `eval`; here the
+    text is parsed with `ast` and only literals are evaluated -- plus the two spellings of the documented `burnin`
+    value, `float('inf')` and `inf` (and their negatives), and `range(...)` / `list(range(...))` of integer literals for
+    `indexes`, which `ast.literal_eval` alone would reject.  Nothing in
+    the line can call a function or reach an attribute."""
+    import ast
+
+    class _Inf(ast.NodeTransformer):
+        def visit_Call(self, node):
+            node.args = [self.visit(a) for a in node.args]
+            name = node.func.id if isinstance(node.func, ast.Name) else None
+            ints = [a.value for a in node.args if isinstance(a, ast.Constant) and type(a.value) is int]
+            if name == "range" and not node.keywords and 1 <= len(node.args) <= 3 and len(ints) == len(node.args):
+                elts = [ast.Constant(v) for v in range(*ints)]     # `indexes` is often written list(range(a, b))
+                return ast.copy_location(ast.List(elts=elts, ctx=ast.Load()), node)
+            if name == "list" and not node.keywords and len(node.args) == 1 and isinstance(node.args[0], (ast.List, ast.Tuple)):
+                return ast.copy_location(ast.List(elts=node.args[0].elts, ctx=ast.Load()), node)
+            if (isinstance(node.func, ast.Name) and node.func.id == "float" and len(node.args) == 1 and not node.keywords
+                    and isinstance(node.args[0], ast.Constant) and isinstance(node.args[0].value, str)):
+                return ast.copy_location(ast.Constant(float(node.args[0].value)), node)
+            raise ValueError("function calls are not allowed in sampler arguments: " + text)
+
+        def visit_Name(self, node):
+            if node.id in ("inf", "Infinity"):
+                return ast.copy_location(ast.Constant(float("inf")), node)
+            if node.id == "nan":
+                return ast.copy_location(ast.Constant(float("nan")), node)
+            raise ValueError("names are not allowed in sampler arguments: " + node.id)
+
+    tree = _Inf().visit(ast.parse(text.strip(), mode="eval"))
+    value = ast.literal_eval(ast.fix_missing_locations(tree))
     if not isinstance(value, dict):
         raise ValueError("sampler arguments must be a dict literal, got: " + text)
     return value

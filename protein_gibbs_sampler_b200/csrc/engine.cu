@@ -113,7 +113,15 @@ static int make_tmap_qkv3(CUtensorMap* m, const void* ptr, uint64_t n_seq, uint6
 }
 
 // ------------------------------------------------------------------------------------- GEMM launch
-static int g_num_sms = 0;
+// SM count of the CURRENT device (cached per device: engines on different GPUs may share a process)
+static int num_sms() {
+  static int cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev < 0 || dev >= 64) { int n = 148; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); return n; }
+  if (!cache[dev]) cudaDeviceGetAttribute(&cache[dev], cudaDevAttrMultiProcessorCount, dev);
+  return cache[dev] ? cache[dev] : 148;
+}
 
 // A GEMM's tiling: tile width and whether a CTA pair (cta_group::2, 256-row tiles) computes it.
 // The B tensor map's box holds bn / cg rows.
@@ -148,14 +156,9 @@ static int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const Ge
     return fail("GEMM output must be 16-byte aligned with a 16-byte multiple row pitch");
   CUtensorMap c;
   TRY(make_tmap_out(&c, p.out, p.M, p.N, p.ldo, epi_out_f16(EPI)));
-  static bool configured = false;
-  if (!configured) {
-    CK(cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                            gemm_smem_bytes(BN, CG)));
-    configured = true;
-  }
+  CK(ensure_dynamic_smem(gemm_tcgen05_kernel<BN, EPI, CG>, gemm_smem_bytes(BN, CG)));
   const int m_tiles = (p.M + kBM * CG - 1) / (kBM * CG), n_tiles = (p.N + BN - 1) / BN;
-  const int groups = std::min(g_num_sms / CG, m_tiles * n_tiles);
+  const int groups = std::min(num_sms() / CG, m_tiles * n_tiles);
   GemmParams q = p;
   q.split = 1;
   if (EPI == EPI_RESID_F32 && p.flags && g_gemm_split) {
@@ -231,7 +234,7 @@ static GemmPlan pick_gemm_plan(int M, int N, int multiple_of) {
   for (int cg = 2; cg >= 1; --cg) {
     if (g_force_cg && cg != g_force_cg) continue;
     if (!g_force_cg && cg == 2 && M <= kBM) continue;
-    const long m_tiles = (M + kBM * cg - 1) / (kBM * cg), slots = g_num_sms / cg;
+    const long m_tiles = (M + kBM * cg - 1) / (kBM * cg), slots = num_sms() / cg;
     for (int i = 0; i < 4; ++i) {
       const int bn = cands[i];
       if (bn % multiple_of) continue;
@@ -478,6 +481,7 @@ static int build_weight_maps(pgibbs_engine* e) {
   return 0;
 }
 
+static int allocate_shape(pgibbs_engine* e, int B, int R, int T);
 static int ensure_shape(pgibbs_engine* e, int B, int R, int T) {
   if (B <= 0 || R <= 0 || T <= 0) return fail("invalid token shape (%d,%d,%d)", B, R, T);
   if (e->cfg.arch != PGIBBS_ARCH_MSA && R != 1) return fail("single-sequence model needs R == 1, got %d", R);
@@ -487,6 +491,16 @@ static int ensure_shape(pgibbs_engine* e, int B, int R, int T) {
   if (B == e->B && R == e->R && T == e->Tu) return 0;
   CK(cudaStreamSynchronize(e->stream));
   free_activations(e);
+  // A failed allocation (e.g. out of memory on a large batch) must not leave the new shape recorded over null or
+  // partial buffers: the next call with the same shape would take the early return above and launch on them.
+  const int rc = allocate_shape(e, B, R, T);
+  if (rc) {
+    free_activations(e);
+    e->B = e->R = e->T = e->Tu = e->n_seq = e->M = 0;
+  }
+  return rc;
+}
+static int allocate_shape(pgibbs_engine* e, int B, int R, int T) {
   const int d = e->cfg.embed_dim, F = e->cfg.ffn_dim, V = e->cfg.vocab;
   e->Tu = T;
   if (e->cfg.arch == PGIBBS_ARCH_ESM1) T += 1;  // the bias key/value slot
@@ -613,11 +627,7 @@ static int attn_mode(int hd) {
 // qkv: fused activation [n_seq*T, 3*H*64]; ctx: [n_seq*T, H*64].
 static int launch_attention_fa(const CUtensorMap& qkv3, const CUtensorMap& ctx3, const __half* qkv, __half* ctx,
                                int n_seq, int T, int H, cudaStream_t st, int reverse = 0) {
-  static bool configured = false;
-  if (!configured) {
-    CK(cudaFuncSetAttribute(attention_fa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFaSmemBytes));
-    configured = true;
-  }
+  CK(ensure_dynamic_smem(attention_fa_kernel, kFaSmemBytes));
   // Trailing rows (T = 128 k + r): r <= 8 -> the kernel's tail warp; r <= 16 -> the mma.sync kernel (second launch);
   // otherwise a normal partly filled tile.  PGIBBS_ATTN_TAIL=0 forces the partly filled tile.
   const int tail = T % 128;
@@ -626,7 +636,7 @@ static int launch_attention_fa(const CUtensorMap& qkv3, const CUtensorMap& ctx3,
   AttnFaParams p{T, H, n_seq, any_tail ? T / 128 : (T + 127) / 128, g_fa_trace, g_attn_stagger,
                  in_kernel ? tail : 0, qkv, ctx, reverse};
   const int n_items = n_seq * H * ((p.n_tiles + 1) / 2);
-  CK(launch_pdl(attention_fa_kernel, dim3(std::min(g_num_sms, n_items)), dim3(kFaThreads), kFaSmemBytes, st, qkv3, ctx3, p));
+  CK(launch_pdl(attention_fa_kernel, dim3(std::min(num_sms(), n_items)), dim3(kFaThreads), kFaSmemBytes, st, qkv3, ctx3, p));
   if (any_tail && !in_kernel) {
     const int d = H * 64;
     AttnParams tp{qkv, ctx, T, 3 * d, d, d, 2 * d, 1, 0, 1, T, T - tail};
@@ -647,11 +657,7 @@ static int run_msa_row_attention(pgibbs_engine* e) {
     MsaRowParams p{e->R, e->T, c.heads, (e->T + 15) & ~15, 0, e->next_dir()};
     p.stages = std::min(8, (227 * 1024 - 2 * kMrQBytes - 2048) / mr_stage_bytes(p.NK));
     const int smem = mr_smem_bytes(p.NK, p.stages);
-    static int configured = 0;
-    if (smem > configured) {
-      CK(cudaFuncSetAttribute(msa_row_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      configured = smem;
-    }
+    CK(ensure_dynamic_smem(msa_row_attention_tc_kernel, smem));
     dim3 grid((e->T + 127) / 128, c.heads, e->B);
     CK(launch_pdl(msa_row_attention_tc_kernel, grid, dim3(kMrThreads), smem, e->stream, e->m_qkv3, e->m_qkv3_keys, e->m_ctx3, p));
     return 0;
@@ -782,12 +788,8 @@ static int forward(pgibbs_engine* e, const Schedule& sched_in, int n_chains, int
     if (e->sc_active) { p.targets = e->sc_targets; p.logp_out = e->sc_logp; }
     const size_t emb_bytes = static_cast<size_t>(c.vocab) * d * sizeof(float);
     p.emb_in_smem = emb_bytes <= 200 * 1024;
-    static bool configured = false;
-    if (!configured) {
-      CK(cudaFuncSetAttribute(head_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
-    }
-    const int grid = std::min(g_num_sms, (rows + 11) / 12);
+    CK(ensure_dynamic_smem(head_sample_kernel, 200 * 1024));
+    const int grid = std::min(num_sms(), (rows + 11) / 12);
     ProfScope ps(e, "head_sample");
     CK(launch_pdl(head_sample_kernel, dim3(grid), dim3(384), p.emb_in_smem ? emb_bytes : 0, st, p));
   }
@@ -904,7 +906,6 @@ int pgibbs_create(const pgibbs_model_config* cfg, int32_t device_id, pgibbs_engi
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device_id));
   if (prop.major != 10) return fail("device %d is sm_%d%d; this engine only runs on sm_100 (B200)", device_id, prop.major, prop.minor);
-  g_num_sms = prop.multiProcessorCount;
   if (const char* f = getenv("PGIBBS_GEMM_CG")) g_force_cg = atoi(f);
   if (const char* f = getenv("PGIBBS_GEMM_SPLIT")) g_gemm_split = atoi(f);
   if (const char* f = getenv("PGIBBS_PDL")) g_pdl = atoi(f);
@@ -1155,7 +1156,7 @@ int pgibbs_forward_logits(pgibbs_engine* e, const int32_t* tokens, int32_t B, in
   TRY(pgibbs_set_tokens(e, tokens, B, R, T));
   if (!logits_out) return fail("null logits_out");
   Schedule s{e->identity_pos, 0, 0, T, 1, 0};
-  TRY(forward(e, s, e->n_seq, 0, false, 0, -1.f, 0, e->logits));
+  TRY(forward(e, s, e->n_seq, 0, false, 0, NAN, 0, e->logits));
   CK(cudaMemcpyAsync(logits_out, e->logits, static_cast<size_t>(e->n_seq) * T * e->cfg.vocab * sizeof(float),
                      cudaMemcpyDefault, e->stream));
   CK(cudaStreamSynchronize(e->stream));
@@ -1190,7 +1191,7 @@ int pgibbs_score(pgibbs_engine* e, const int32_t* targets, int32_t mask, int32_t
     CK(cudaGetLastError());
   }
   e->sc_active = true;
-  const int rc = forward(e, s, n_chains, 0, false, 0, -1.f, 0, nullptr);
+  const int rc = forward(e, s, n_chains, 0, false, 0, NAN, 0, nullptr);
   e->sc_active = false;
   if (rc) return rc;
   CK(cudaMemcpyAsync(logp_out, e->sc_logp, rows * sizeof(float), cudaMemcpyDefault, e->stream));
@@ -1293,7 +1294,6 @@ static int op_device(int device_id) {
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device_id));
   if (prop.major != 10) return fail("device %d is not sm_100", device_id);
-  g_num_sms = prop.multiProcessorCount;
   return 0;
 }
 

@@ -297,12 +297,8 @@ static const char* launch_msa_col_attention(const AttnParams& p, int groups, int
   const int hg = H % 4 == 0 ? 4 : (H % 2 == 0 ? 2 : 0);
   if (!hg) return "";
   const size_t smem = static_cast<size_t>(3) * hg * 32 * (64 + 8) * sizeof(__half);
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(msa_col_attention_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 4 * 32 * 72 * 2) != cudaSuccess)
-      return "cudaFuncSetAttribute(msa_col_attention_kernel) failed";
-    configured = true;
-  }
+  if (ensure_dynamic_smem(msa_col_attention_kernel<4>, 3 * 4 * 32 * 72 * 2) != cudaSuccess)
+    return "cudaFuncSetAttribute(msa_col_attention_kernel) failed";
   dim3 grid(groups, H / hg);
   if (hg == 4) msa_col_attention_kernel<4><<<grid, 256, smem, st>>>(p);
   else msa_col_attention_kernel<2><<<grid, 128, smem, st>>>(p);
@@ -321,13 +317,8 @@ static const char* launch_msa_row_attention_t(const __half* qkv, __half* ctx, fl
   const int Cpad = tiles * 64;
   const size_t smem = (static_cast<size_t>(64) * (Cpad + 8) + 2 * 64 * (DH + 8)) * sizeof(__half);
   if (smem > 227 * 1024) return "MSA too wide for the row-attention kernel's shared-memory softmax tile";
-  static size_t configured = 0;
-  if (smem > configured) {
-    if (cudaFuncSetAttribute(msa_row_pv_kernel<DH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             static_cast<int>(smem)) != cudaSuccess)
-      return "cudaFuncSetAttribute(msa_row_pv_kernel) failed";
-    configured = smem;
-  }
+  if (ensure_dynamic_smem(msa_row_pv_kernel<DH>, static_cast<int>(smem)) != cudaSuccess)
+    return "cudaFuncSetAttribute(msa_row_pv_kernel) failed";
   const int rows_per_group = R >= 8 ? 4 : 1;
   const int groups = (R + rows_per_group - 1) / rows_per_group;
   msa_row_pv_kernel<DH><<<dim3(tiles, groups, B * H), 128, smem, st>>>(qkv, scores, ctx, R, C, H, ld, d, 2 * d,

@@ -9,6 +9,34 @@
 
 namespace pg {
 
+// Host side: opt a kernel into `bytes` of dynamic shared memory on the CURRENT device.  Function attributes are per
+// device (context), so the high-water mark is kept per (device, kernel) -- a process-wide "configured" flag would
+// leave the second GPU of a process unconfigured.
+inline cudaError_t ensure_dynamic_smem(const void* func, int bytes) {
+  constexpr int kMaxDev = 64, kMaxFuncs = 128;
+  static const void* funcs[kMaxFuncs];
+  static int high[kMaxFuncs][kMaxDev];
+  static int n_funcs = 0;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  int fi = 0;
+  while (fi < n_funcs && funcs[fi] != func) ++fi;
+  if (fi == n_funcs) {
+    if (n_funcs == kMaxFuncs || dev >= kMaxDev) return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    funcs[n_funcs++] = func;
+  }
+  if (dev >= kMaxDev) return cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (bytes <= high[fi][dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) high[fi][dev] = bytes;
+  return e;
+}
+template <typename... A>
+inline cudaError_t ensure_dynamic_smem(void (*kernel)(A...), int bytes) {
+  return ensure_dynamic_smem(reinterpret_cast<const void*>(kernel), bytes);
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -299,7 +299,7 @@ __device__ __forceinline__ int generate_step_warp(float mine, float extra, int l
     return id >= 32 ? hi : lo;
   };
   float la = fetch(id_a), lb = fetch(id_b);
-  if (temperature > 0.f) { la = __fdiv_rn(la, temperature); lb = __fdiv_rn(lb, temperature); }
+  if (temperature == temperature) { la = __fdiv_rn(la, temperature); lb = __fdiv_rn(lb, temperature); }  // NaN = None
   if (!has_a) la = -INFINITY;
   if (!has_b) lb = -INFINITY;
   // rank = position in the descending top-k order (ties: lower candidate slot first)
@@ -394,7 +394,7 @@ struct HeadParams {
   int top_k;                 // effective k for this iteration (already resolved against burn-in), <= n_valid
   int top_k_raw;             // with sched.iter_dev: the caller's top_k and burn-in, resolved per iteration on the device
   long long burnin;
-  float temperature;         // <= 0 : none
+  float temperature;         // NaN : none (any other value divides the logits, as the reference does)
   const float* noise;        // replay: [rows, noise_stride] Exp(1) draws for this iteration, slot j <-> j-th largest
   int noise_stride;
   unsigned long long seed;   // device RNG otherwise

@@ -119,15 +119,27 @@ class Engine:
             return 0
         return int(min(max(math.ceil(b), 0), INT64_MAX))
 
+    @staticmethod
+    def _temperature(t):
+        """None -> NaN (the ABI's "no temperature"); any other value divides the logits as the reference's
+        generate_step does (esm_sampler.py:24-25), including negative ones.  0 would make every logit +-inf / nan,
+        which torch's Categorical rejects in the reference; it is rejected here too."""
+        if t is None:
+            return float("nan")
+        t = float(t)
+        if t == 0.0 or t != t:
+            raise ValueError("temperature must be a non-zero number or None, got %r" % (t,))
+        return t
+
     def run(self, first_iter, num_iters, burnin, top_k, temperature, mask, valid_ids):
         v = np.ascontiguousarray(valid_ids, dtype=np.int32)
-        temp = -1.0 if temperature is None else float(temperature)
+        temp = self._temperature(temperature)
         check(self.lib.pgibbs_run(self.h, first_iter, num_iters, self._burnin(burnin), int(top_k), temp, int(bool(mask)),
                                   _ptr(v), v.size))
 
     def run_single(self, first_iter, num_iters, burnin, top_k, temperature, mask_row, target_row, valid_ids):
         v = np.ascontiguousarray(valid_ids, dtype=np.int32)
-        temp = -1.0 if temperature is None else float(temperature)
+        temp = self._temperature(temperature)
         check(self.lib.pgibbs_run_single(self.h, first_iter, num_iters, self._burnin(burnin), int(top_k), temp,
                                          int(mask_row), int(target_row), _ptr(v), v.size))
 
@@ -211,5 +223,5 @@ def op_sample(logits, noise, valid_ids, top_k=0, temperature=None, device_id=0):
     n = None if noise is None else torch.as_tensor(noise, dtype=torch.float32).contiguous()
     out = torch.empty(rows, dtype=torch.int32)
     check(lib.pgibbs_op_sample(device_id, _ptr(l), None if n is None else _ptr(n), rows, V, _ptr(v), v.size, int(top_k),
-                               -1.0 if temperature is None else float(temperature), _ptr(out)))
+                               Engine._temperature(temperature), _ptr(out)))
     return out.to(torch.int64)

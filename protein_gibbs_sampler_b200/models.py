@@ -18,15 +18,68 @@ from .engine import Engine
 from .weights import synthetic_state_dict
 
 
-def upgrade_state_dict(sd):
-    """Strip the prefixes fair-esm checkpoints carry (esm.pretrained's key rewriting)."""
+def upgrade_state_dict(sd, arch=None):
+    """Key rewriting of fair-esm's checkpoint loaders (``esm/pretrained.py``: ``_load_model_and_alphabet_core_v1`` /
+    ``_core_v2``), per architecture -- the reference reaches it through ``esm.pretrained.*`` at models.py:61-86.
+
+    * ``roberta_large`` (ESM-1b / ESM-1v): drop ``encoder.`` / ``sentence_encoder.``; the ``<mask>`` row of
+      ``embed_tokens.weight`` is zeroed ("for token drop") -- the tied LM head then gives ``<mask>`` the bare output
+      bias, which enters every full-vocabulary log_softmax of the likelihood path.
+    * ``protein_bert_base`` (ESM-1: esm1_t6 / t12 / t34): drop ``decoder.``.
+    * ``msa_transformer``: the published checkpoints name the two axial attentions the other way round, so ``row`` and
+      ``column`` are SWAPPED in every key before the prefixes are dropped.  Both blocks are d x d: without the swap
+      the weights load without an error and every result is silently wrong.
+    * ESM-2 (``_core_v2``): drop ``encoder.sentence_encoder.`` / ``encoder.`` at the start of the key.
+    ``arch`` is this package's architecture name (``cfg["arch"]``); ``None`` only strips prefixes (already-upgraded
+    or synthetic dicts pass through unchanged)."""
+    def strip_all(key, marker):
+        # fair-esm: "".join(s.split(marker)[1:] if marker[:-1] in s else s) -- everything up to and including the
+        # first occurrence goes, later occurrences are removed as well
+        return "".join(key.split(marker)[1:]) if marker in key else key
+
     out = {}
     for k, v in sd.items():
-        k = re.sub(r"^(encoder\.)?sentence_encoder\.", "", k)
-        k = re.sub(r"^encoder\.", "", k)
+        if arch == "msa_transformer":
+            k = k.replace("row", "column") if "row" in k else k.replace("column", "row")
+            k = strip_all(strip_all(k, "sentence_encoder."), "encoder.")
+        elif arch == "roberta_large":
+            k = strip_all(strip_all(k, "sentence_encoder."), "encoder.")
+        elif arch == "esm1":
+            k = strip_all(k, "decoder.")
+        else:  # esm2, or unknown: prefixes at the start of the key only
+            k = re.sub(r"^(model\.)?(encoder\.sentence_encoder\.|encoder\.)", "", k)
         k = re.sub(r"^msa\.", "", k)
         out[k] = v
+    if arch == "roberta_large" and "embed_tokens.weight" in out:
+        w = out["embed_tokens.weight"].clone()
+        w[32].zero_()   # alphabet.mask_idx of the "ESM-1b" alphabet
+        out["embed_tokens.weight"] = w
+        if "lm_head.weight" in out:
+            out["lm_head.weight"] = w
     return out
+
+
+def load_checkpoint(path, arch):
+    """``model`` state dict of a fair-esm ``.pt`` checkpoint, upgraded for ``arch``.  Loaded with
+    ``weights_only=True`` (tensors, containers and the ``argparse.Namespace`` fair-esm stores its hyper-parameters
+    in): a checkpoint is user-supplied data and the full pickle protocol can run arbitrary code.  Set
+    ``PGIBBS_TRUST_CHECKPOINT=1`` to fall back to the unrestricted loader for files you trust."""
+    import argparse
+    import os
+    try:
+        with torch.serialization.safe_globals([argparse.Namespace]):
+            blob = torch.load(path, map_location="cpu", weights_only=True)
+    except Exception as exc:
+        if os.environ.get("PGIBBS_TRUST_CHECKPOINT") != "1":
+            raise Exception("checkpoint %s needs more than tensors and argparse.Namespace to unpickle (%s); "
+                            "set PGIBBS_TRUST_CHECKPOINT=1 if the file is trusted" % (path, exc))
+        blob = torch.load(path, map_location="cpu", weights_only=False)
+    ck_arch = getattr(blob.get("args", None), "arch", None) if isinstance(blob, dict) else None
+    expected = {"roberta_large": "roberta_large", "esm1": "protein_bert_base", "msa_transformer": "msa_transformer"}
+    if ck_arch is not None and arch in expected and ck_arch != expected[arch]:
+        raise Exception("checkpoint %s holds a '%s' model, this class expects '%s'" % (path, ck_arch, expected[arch]))
+    sd = blob["model"] if isinstance(blob, dict) and "model" in blob else blob
+    return upgrade_state_dict(sd, arch)
 
 
 class EngineModule:
@@ -80,8 +133,7 @@ class _Triple:
         self.cfg = get_config(self.config_name, **cfg_overrides)
         self.alphabet = self.alphabet_factory()
         if checkpoint is not None:
-            blob = torch.load(checkpoint, map_location="cpu", weights_only=False)
-            state_dict = upgrade_state_dict(blob["model"] if "model" in blob else blob)
+            state_dict = load_checkpoint(checkpoint, self.cfg["arch"])
         if state_dict is None:
             state_dict = synthetic_state_dict(self.cfg, seed)
         self.model = EngineModule(self.cfg, self.alphabet, state_dict)

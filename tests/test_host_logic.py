@@ -214,6 +214,83 @@ def test_upgrade_state_dict_strips_fair_esm_prefixes():
     assert set(models.upgrade_state_dict(sd)) == {"layers.0.fc1.weight", "lm_head.bias", "embed_tokens.weight"}
 
 
+def _as_published(sd, arch):
+    """Rename an engine-side (= post-upgrade fair-esm) state dict the way the published checkpoints name their keys:
+    the inverse of esm/pretrained.py's key rewriting."""
+    out = {}
+    for k, v in sd.items():
+        if arch == "msa_transformer":
+            k = k.replace("row", "column") if "row" in k else k.replace("column", "row")
+        if arch == "esm1":
+            k = "decoder." + k
+        elif arch == "esm2":
+            k = ("encoder." if k.startswith("lm_head") else "encoder.sentence_encoder.") + k
+        else:
+            k = ("encoder." if k.startswith("lm_head") else "encoder.sentence_encoder.") + k
+        out[k] = v
+    return out
+
+
+@pytest.mark.parametrize("arch", ["roberta_large", "esm2", "esm1", "msa_transformer"])
+def test_upgrade_state_dict_per_architecture(arch, tmp_path):
+    """fair-esm's per-architecture key rewriting (esm/pretrained.py, reached by the reference at models.py:61-86): the
+    MSA Transformer's published keys have row / column attention swapped, ESM-1 keys carry `decoder.`, ESM-1b zeroes the
+    <mask> embedding row.  A checkpoint written with published names must load back to exactly the engine's tensors."""
+    import argparse
+    import torch
+    from protein_gibbs_sampler_b200.config import tiny_config
+    from protein_gibbs_sampler_b200.weights import synthetic_state_dict
+    cfg = tiny_config(arch, 2, 64, 2, 128)
+    sd = {k: v for k, v in synthetic_state_dict(cfg, 1).items()}
+    published = _as_published(sd, arch)
+    if arch == "msa_transformer":
+        # the swap is real: a published "column" key holds what the model calls the tied ROW attention
+        assert "encoder.sentence_encoder.layers.0.column_self_attention.layer.q_proj.weight" in published
+        assert torch.equal(published["encoder.sentence_encoder.layers.0.column_self_attention.layer.q_proj.weight"],
+                           sd["layers.0.row_self_attention.layer.q_proj.weight"])
+    if arch == "esm1":
+        published["decoder.embed_positions._float_tensor"] = torch.zeros(1)
+    up = models.upgrade_state_dict(published, arch)
+    assert set(sd) <= set(up)
+    for k, v in sd.items():
+        if arch == "roberta_large" and k in ("embed_tokens.weight", "lm_head.weight"):
+            assert torch.equal(up[k][:32], v[:32]) and not up[k][32].any() and v[32].any()
+        else:
+            assert torch.equal(up[k], v), k
+    # the .pt path: fair-esm checkpoints are {"args": Namespace(arch=...), "model": state dict}
+    ck_arch = {"roberta_large": "roberta_large", "esm1": "protein_bert_base", "msa_transformer": "msa_transformer",
+               "esm2": None}[arch]
+    blob = {"model": published}
+    if ck_arch:
+        blob["args"] = argparse.Namespace(arch=ck_arch, layers=2)
+    path = str(tmp_path / "ck.pt")
+    torch.save(blob, path)
+    loaded = models.load_checkpoint(path, arch)
+    assert all(torch.equal(loaded[k], up[k]) for k in up)
+    if ck_arch:
+        other = "esm1" if arch != "esm1" else "roberta_large"
+        with pytest.raises(Exception, match="expects"):
+            models.load_checkpoint(path, other)
+
+
+def test_checkpoint_loader_refuses_arbitrary_pickles(tmp_path, monkeypatch):
+    """A .pt file is user-supplied data: objects beyond tensors / containers / argparse.Namespace are refused unless
+    PGIBBS_TRUST_CHECKPOINT=1."""
+    import torch
+
+    path = str(tmp_path / "evil.pt")
+    torch.save({"model": {"w": torch.zeros(1)}, "hook": _Unpicklable()}, path)
+    monkeypatch.delenv("PGIBBS_TRUST_CHECKPOINT", raising=False)
+    with pytest.raises(Exception, match="PGIBBS_TRUST_CHECKPOINT"):
+        models.load_checkpoint(path, "esm2")
+    monkeypatch.setenv("PGIBBS_TRUST_CHECKPOINT", "1")
+    assert set(models.load_checkpoint(path, "esm2")) == {"w"}
+
+
+class _Unpicklable:
+    pass
+
+
 def test_esm1_alphabet_ids_pinned_by_reference_fixtures():
     """ESM-1 alphabet (esm6 / esm12 / esm34): <cls>=32, <mask>=33, A=5 (`/root/reference/test/test_esm_sampler.py:43-66`),
     bos only, 35 tokens; identical to the oracle's restatement of `esm.data.Alphabet.from_architecture("ESM-1")`."""
