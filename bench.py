@@ -1,12 +1,14 @@
 """Gibbs-iteration throughput benchmark (BASELINE.json metric) -- one JSON line on stdout from rank 0.
 
-Workload at every N: BASELINE.json configs[1] per GPU -- ESM-1b 650M (33 x 1280, 20 heads, FFN 5120), 64
+Headline workload at every N: BASELINE.json configs[1] per GPU -- ESM-1b 650M (33 x 1280, 20 heads, FFN 5120), 64
 independent chains of L=256 (T=258 tokens), top_k=3 with burnin=0, all 256 positions resampled each iteration,
 <mask> scatter on.  A "step" is one Gibbs iteration over the batch.  Chains shard across GPUs with no data-path
-collective ("weak" scaling: 64 chains per GPU); NCCL is used once, to broadcast the weights from rank 0.
+collective ("weak" scaling: 64 chains per GPU); NCCL is used once, to broadcast the packed weight blob from rank 0.
+The per-GPU shards of the other BASELINE configs (3, 4, 5) and the split-operand precision mode are timed in the same
+run and reported under "other_configs" (5 timed steps each).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]                 # this engine
-  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # the reference's CPU loop (oracle port)
+  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W] # the reference's CPU loop on the host cores
 """
 import argparse
 import json
@@ -39,13 +41,20 @@ def workload_config(n_gpus):
         "parallelism": "chains sharded, %d x 64" % n_gpus,
         "l2": "no flush: per-iteration working set (1.3 GB fp16 weights + >1 GB activations) >> 126 MB L2",
         "weights": "synthetic seeded N(0,0.02) (no pretrained checkpoints offline)",
+        "precision": "fast (one tensor-core pass of fp16 operands per GEMM); split-operand mode under other_configs",
     }
 
 
 def algorithmic_flops_per_iter(cfg, B, T):
+    """GEMMs + attention matmuls, 2 FLOP per MAC, LM head over all tokens as the reference computes it."""
     d, F, V, L = cfg["embed_dim"], cfg["ffn_dim"], cfg["vocab"], cfg["layers"]
     f_token = L * (2 * (4 * d * d + 2 * d * F) + 4 * T * d) + 2 * (d * d + d * V)
     return B * T * f_token
+
+
+def msa_flops_per_iter(cfg, B, R, C):
+    d, F, V, L = cfg["embed_dim"], cfg["ffn_dim"], cfg["vocab"], cfg["layers"]
+    return B * R * C * (L * (2 * (8 * d * d + 2 * d * F) + 4 * C * d + 4 * R * d) + 2 * (d * d + d * V))
 
 
 def seeds(n, length, seed=1234):
@@ -82,6 +91,7 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+        return self
 
     def stop(self):
         if not self.proc:
@@ -109,75 +119,201 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------- CPU arms
 _CPU_MODEL = None
+REF_SAMPLE_CHAINS = 4          # of the 64 chains of one GPU's batch; the loop's cost is linear in the chain count
+
+
+def _host_threads():
+    """All the host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to every rank)."""
+    import torch
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        pass
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
+
+
+def _reference_sampler_class():
+    """The UNMODIFIED reference sampler (`pgen.esm_sampler.ESM_sampler`, installed with pip from /root/reference into
+    baseline/_ref by __graft_entry__.build(); git-ignored, ships to the GPU box), or None -> the oracle's port of the
+    same loop.  Either way the forward is the fp32 eager restatement in oracle/fair_esm.py: fair-esm itself cannot be
+    installed offline."""
+    for p in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference/src"):
+        if os.path.isdir(os.path.join(p, "pgen")):
+            sys.path.insert(0, p)
+            try:
+                from pgen.esm_sampler import ESM_sampler as RefSampler
+                return RefSampler, p
+            except Exception:
+                sys.path.remove(p)
+    return None, None
 
 
 def cpu_reference_run(n_chains, n_iters):
-    """The reference's loop (oracle port: per-residue generate_step on the host + fp32 eager forward),
-    on all the host threads torch uses by default."""
+    """One bounded sample of the C2 workload on the host: `n_chains` chains x `n_iters` iterations of the reference
+    loop (per-residue generate_step + one fp32 forward per iteration).  Returns (seconds, threads, kind)."""
     global _CPU_MODEL
     import torch
     from oracle.fair_esm import OracleModel
-    from oracle.gibbs_loop import esm_generate
     from protein_gibbs_sampler_b200.config import get_config
     from protein_gibbs_sampler_b200.weights import synthetic_state_dict
+    threads = _host_threads()
     if _CPU_MODEL is None:
         cfg = get_config(MODEL)
         _CPU_MODEL = OracleModel(cfg, synthetic_state_dict(cfg, 0))
     model = _CPU_MODEL
+    ref_cls, _ = _reference_sampler_class()
     random.seed(0)
     torch.manual_seed(0)
+    kw = dict(batch_size=n_chains, num_iters=n_iters, top_k=TOP_K, burnin=BURNIN)
     t0 = time.perf_counter()
-    esm_generate(model, n_chains, seeds(n_chains, SEQ_LEN), batch_size=n_chains, num_iters=n_iters, top_k=TOP_K,
-                 burnin=BURNIN)
+    if ref_cls is not None:
+        out = ref_cls(model, device="cpu").generate(n_chains, seeds(n_chains, SEQ_LEN), show_progress_bar=False, **kw)
+        kind = "reference"
+    else:
+        from oracle.gibbs_loop import esm_generate
+        out = esm_generate(model, n_chains, seeds(n_chains, SEQ_LEN), **kw)
+        kind = "port"
     dt = time.perf_counter() - t0
-    return dt, torch.get_num_threads()
+    assert len(out) == n_chains and all(len(s) == SEQ_LEN for s in out)
+    return dt, threads, kind
+
+
+def _cpu_kind_note(kind):
+    return ("unmodified reference sampler loop (pgen.esm_sampler.ESM_sampler.generate from baseline/_ref) driving the "
+            "fp32 eager forward of oracle/fair_esm.py" if kind == "reference" else
+            "oracle/gibbs_loop.py port of the reference sampler loop + the fp32 eager forward of oracle/fair_esm.py") + \
+        " (fair-esm is not installable offline)"
 
 
 def cpu_baseline_sample():
     """Bounded sample: 4 of the 64 chains for 1 iteration (~1.4 TFLOP of fp32 GEMM + 1024 generate_step calls)."""
-    n_chains, n_iters = 4, 1
-    dt, threads = cpu_reference_run(n_chains, n_iters)
-    iters_per_s = (n_iters / dt) * (n_chains / CHAINS_PER_GPU)  # cost is linear in the number of chains
-    return {"value": iters_per_s, "unit": "iters/s (64-chain iterations)", "cores": threads, "kind": "port",
-            "sample": "%d of 64 chains x %d iteration(s) of the same workload in %.1f s, scaled linearly in chains; "
-                      "reference sampler loop restated in oracle/gibbs_loop.py + fp32 eager forward "
-                      "(fair-esm is not installable offline)" % (n_chains, n_iters, dt)}
+    n_chains, n_iters = REF_SAMPLE_CHAINS, 1
+    cpu_reference_run(n_chains, n_iters)                  # page in the weights / warm the thread pool
+    dt, threads, kind = cpu_reference_run(n_chains, n_iters)
+    iters_per_s = (n_iters / dt) * (n_chains / CHAINS_PER_GPU)
+    return {"value": iters_per_s, "unit": "iters/s (64-chain iterations)", "cores": threads, "kind": kind,
+            "sample": "%d of 64 chains x %d iteration(s) of the same workload measured in %.2f s and scaled x%d "
+                      "(linear in chains); %s" % (n_chains, n_iters, dt, CHAINS_PER_GPU // n_chains, _cpu_kind_note(kind))}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_chains = 4
+    n_chains = REF_SAMPLE_CHAINS
+    scale = CHAINS_PER_GPU // n_chains
     times = []
     for i in range(args.warmup + args.steps):
-        dt, threads = cpu_reference_run(n_chains, 1)
+        dt, threads, kind = cpu_reference_run(n_chains, 1)
         if i >= args.warmup:
             times.append(dt)
     dt = sum(times) / len(times)
-    # one 64-chain iteration costs 16x the 4-chain sample; N GPUs' worth of chains cost N x that on the same host
-    value = (1.0 / dt) * (n_chains / CHAINS_PER_GPU)
+    # one 64-chain iteration costs `scale` x the sample on the same host cores
+    value = (1.0 / dt) / scale
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "steps": args.steps, "warmup": args.warmup,
+        # what was actually timed: one step = the bounded sample; the 64-chain figure is `value`
+        "ms_per_step": 1000.0 * dt, "ms_per_step_is": "measured sample (%d of 64 chains x 1 iteration)" % n_chains,
+        "sample_scale": scale, "ms_per_64_chain_iteration_extrapolated": 1000.0 * dt * scale,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "each step = %d of 64 chains x 1 iteration (%.1f s), scaled linearly in chains"
-                                   % (n_chains, dt)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": "each step = %d of 64 chains x 1 iteration, measured %.2f s, value scaled x%d "
+                                   "(linear in chains); %s" % (n_chains, dt, scale, _cpu_kind_note(kind))},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+class Timer:
+    """Device-timed region on the engine's stream, max over ranks."""
+
+    def __init__(self, torch, dist, world, dev, stream):
+        self.torch, self.dist, self.world, self.dev, self.stream = torch, dist, world, dev, stream
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, fn, profiler=False):
+        torch = self.torch
+        self.barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        if profiler:
+            torch.cuda.profiler.start()   # `ncu --profile-from-start off` then captures exactly the timed region
+        ev0.record(self.stream)
+        fn()
+        ev1.record(self.stream)
+        self.barrier()
+        if profiler:
+            torch.cuda.profiler.stop()
+        host_ms = (time.perf_counter() - t0) * 1000.0
+        ms = ev0.elapsed_time(ev1)
+        # the device interval can never exceed the host wall clock around it by more than jitter
+        assert ms <= host_ms * 1.05 + 1.0 and ms >= 0.5 * host_ms - 1.0, (ms, host_ms)
+        return self.max_over_ranks(ms)
+
+    def max_over_ranks(self, v):
+        if self.world > 1:
+            t = self.torch.tensor([v], device=self.dev, dtype=self.torch.float64)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            v = t.item()
+        return v
+
+
+def _model_on_ranks(models_mod, cls, cfg, world, rank, dev, precision="fast"):
+    """Rank 0 creates the synthetic weights; one NCCL broadcast of the packed blob ships them (the only collective on
+    the data path).  Split-operand precision needs the fp32 weights, so its blob is not packed to fp16."""
+    from protein_gibbs_sampler_b200.parallel import broadcast_weights
+    from protein_gibbs_sampler_b200.weights import synthetic_state_dict
+    if world > 1:
+        sd = synthetic_state_dict(cfg, 0) if rank == 0 else None
+        sd = broadcast_weights(cfg, sd, src=0, device=dev, gemm_fp16=(precision == "fast"))
+    else:
+        sd = synthetic_state_dict(cfg, 0)
+    return cls(state_dict=sd, precision=precision)
+
+
+def _time_single(timer, sampler_cls, model, local, rank, B, L, top_k, burnin, num_positions, W, K, profiler=False):
+    """Device-resident Gibbs iterations of a single-sequence config: tokens + schedule in HBM before the clock starts."""
+    s = sampler_cls(model, device="cuda:%d" % local, rng="device")
+    eng = model.model.engine
+    eng.set_stream(timer.stream.cuda_stream)
+    toks = model.batch_converter([(str(i), q) for i, q in enumerate(seeds(B, L, 1234 + rank))])[2]
+    idx, _ = s.calculate_indexes(None, 0, L, False)
+    random.seed(rank)
+    plan, _ = s.plan_positions(B, idx, -1, num_positions, False, W + K)
+    eng.set_tokens(toks)
+    eng.set_schedule(plan.positions, plan.n_iters, plan.P, plan.iter_stride, plan.chain_stride)
+    eng.set_noise(None)
+    eng.set_device_rng(1234 + rank)
+    eng.run(0, W, burnin, top_k, None, True, s.valid_aa_idx)
+    launches0 = eng.launch_count()
+    ms = timer.run(lambda: eng.run(W, K, burnin, top_k, None, True, s.valid_aa_idx), profiler)
+    return s, plan, toks, ms, eng.launch_count() - launches0
+
+
+def _other_config_entry(name, workload, ms, K, flops, peaks, world, clock):
+    tf = flops / (ms / K / 1000.0) / 1e12
+    return {"workload": workload, "steps": K, "ms_per_step": ms / K, "iters_per_sec": world * K / (ms / 1000.0),
+            "n_gpus": world, "algorithmic_tflop_per_iter_per_gpu": flops / 1e12, "achieved_tflops_per_gpu": tf,
+            "frac_of_sustained_peak": tf / peaks["tensor"], "clocks": clock}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from protein_gibbs_sampler_b200 import models
     from protein_gibbs_sampler_b200.config import get_config
+    from protein_gibbs_sampler_b200.esm_msa_sampler import ESM_MSA_sampler
     from protein_gibbs_sampler_b200.esm_sampler import ESM_sampler
-    from protein_gibbs_sampler_b200.weights import synthetic_state_dict
+    from protein_gibbs_sampler_b200.parallel import shard_sampler
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -188,92 +324,57 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    cfg = get_config(MODEL)
-
-    # ---- weights: rank 0 creates them, one NCCL broadcast ships them (the only collective on this path)
-    if world > 1:
-        sd = synthetic_state_dict(cfg, 0) if rank == 0 else None
-        meta = [{k: tuple(v.shape) for k, v in sd.items() if k != "lm_head.weight"}] if rank == 0 else [None]
-        dist.broadcast_object_list(meta, src=0)
-        gsd = {}
-        for k, shape in meta[0].items():
-            t = sd[k].to(dev) if rank == 0 else torch.empty(shape, dtype=torch.float32, device=dev)
-            dist.broadcast(t, src=0)
-            gsd[k] = t
-        sd = gsd
-    else:
-        sd = synthetic_state_dict(cfg, 0)
-    model = models.ESM1b(state_dict=sd)
-    sampler = ESM_sampler(model, device="cuda:%d" % local, rng="device")
-    del sd
-    engine = model.model.engine
-    # time on the stream the kernels are launched on: a dedicated torch stream shared with the engine
+    # time on the stream the kernels are launched on: a dedicated torch stream shared with the engines
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    engine.set_stream(stream.cuda_stream)
+    timer = Timer(torch, dist, world, dev, stream)
+    peaks = measured_peaks()
+    cfg = get_config(MODEL)
+    model = _model_on_ranks(models, models.ESM1b, cfg, world, rank, dev)
 
     B, T = CHAINS_PER_GPU, SEQ_LEN + 2
     K, W = args.steps, args.warmup
-    my_seeds = seeds(B * world, SEQ_LEN)[rank * B:(rank + 1) * B]
-    tokens = model.batch_converter([(str(i), s) for i, s in enumerate(my_seeds)])[2]
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident throughput: tokens + schedule already in HBM when the timed region starts
-    indexes, _ = sampler.calculate_indexes(None, 0, SEQ_LEN, False)
-    plan, _ = sampler.plan_positions(B, indexes, -1, 0, False, W + K)
-    engine.set_tokens(tokens)
-    engine.set_schedule(plan.positions, plan.n_iters, plan.P, plan.iter_stride, plan.chain_stride)
-    engine.set_noise(None)
-    engine.set_device_rng(1234 + rank)
-    engine.run(0, W, BURNIN, TOP_K, None, True, sampler.valid_aa_idx)
-    barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    launches0 = engine.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_host0 = time.perf_counter()
-    torch.cuda.profiler.start()   # `ncu --profile-from-start off` then captures exactly the timed region
-    ev0.record(stream)
-    engine.run(W, K, BURNIN, TOP_K, None, True, sampler.valid_aa_idx)
-    ev1.record(stream)
-    barrier()
-    torch.cuda.profiler.stop()
-    host_ms = (time.perf_counter() - t_host0) * 1000.0
-    ms = ev0.elapsed_time(ev1)
-    # the device interval can never exceed the host wall clock around it by more than jitter
-    assert ms <= host_ms * 1.05 + 1.0 and ms >= 0.5 * host_ms, (ms, host_ms)
-    launches = engine.launch_count() - launches0
+    # ---- headline: device-resident throughput of config 2
+    clocks = ClockSampler(local).start() if rank == 0 else None
+    sampler, plan, tokens, ms, launches = _time_single(timer, ESM_sampler, model, local, rank, B, SEQ_LEN, TOP_K, BURNIN,
+                                                       0, W, K, profiler=True)
     clock_info = clocks.stop() if rank == 0 else None
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
+    engine = model.model.engine
     value = world * K / (ms / 1000.0)
 
-    # ---- end to end through the public API: host strings in, host strings out (H2D + D2H inside)
-    random.seed(rank)
-    torch.manual_seed(rank)
-    sampler.generate(B, my_seeds, batch_size=B, num_iters=min(W, 3), top_k=TOP_K, burnin=BURNIN,
-                     show_progress_bar=False)
-    barrier()
-    t0 = time.perf_counter()
-    out = sampler.generate(B, my_seeds, batch_size=B, num_iters=K, top_k=TOP_K, burnin=BURNIN,
-                           show_progress_bar=False)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    assert len(out) == B and all(len(s) == SEQ_LEN for s in out)
+    # ---- end to end through the public API: host strings in, host strings out (H2D + D2H inside).  At N > 1 this is
+    # the product's sharded path: every rank calls the SAME generate(N*64 chains) on a parallel.shard_sampler, runs
+    # its 64-chain slice and the final tokens are all-gathered once.
+    all_seeds = seeds(B * world, SEQ_LEN)
     if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = t.item()
+        shard_sampler(sampler)
+
+    def e2e_generate(n_iters):
+        random.seed(0)
+        torch.manual_seed(0)
+        return sampler.generate(B * world, all_seeds, batch_size=B * world, num_iters=n_iters, top_k=TOP_K, burnin=BURNIN,
+                                show_progress_bar=False)
+
+    e2e_generate(min(W, 3))
+    timer.barrier()
+    t0 = time.perf_counter()
+    out = e2e_generate(K)
+    torch.cuda.synchronize()
+    e2e_s = timer.max_over_ranks(time.perf_counter() - t0)
+    assert len(out) == B * world and all(len(s) == SEQ_LEN for s in out)
     e2e_value = world * K / e2e_s
     h2d = (B * T * 4 + plan.P * 4 + len(sampler.valid_aa_idx) * 4) / K   # tokens + schedule + candidate ids, once per call
     d2h = (B * T * 4) / K
+    sharded_check = None
+    if world > 1:
+        # the sharded run returns what ONE GPU computes for all N*64 chains: rank 0 re-runs a short job unsharded
+        short = e2e_generate(3)
+        sampler.shard = None
+        if rank == 0:
+            sharded_check = {"iters": 3, "chains": B * world, "equal_to_single_gpu": e2e_generate(3) == short}
+            assert sharded_check["equal_to_single_gpu"], "sharded generate differs from the single-GPU run"
+        timer.barrier()
 
     # ---- per-kernel-class timing (separate pass with CUDA events around every launch) for the roofline
     roofline = None
@@ -281,17 +382,22 @@ def run_ours(args):
         n_prof = min(K, 5)
         engine.set_tokens(tokens)
         engine.set_schedule(plan.positions, plan.n_iters, plan.P, plan.iter_stride, plan.chain_stride)
+        engine.set_chain_offset(0)
         engine.profile_enable(True)
         engine.run(W, n_prof, BURNIN, TOP_K, None, True, sampler.valid_aa_idx)
         engine.sync()
         prof = engine.profile_read()
         engine.profile_enable(False)
-        peaks = measured_peaks()
         M, d, F = B * T, cfg["embed_dim"], cfg["ffn_dim"]
         gemm_flops = {"gemm_qkv": 2.0 * M * 3 * d * d, "gemm_out": 2.0 * M * d * d, "gemm_fc1": 2.0 * M * d * F,
-                      "gemm_fc2": 2.0 * M * d * F, "gemm_head": 2.0 * (B * SEQ_LEN) * d * d}
+                      "gemm_fc2": 2.0 * M * d * F, "gemm_head": 2.0 * (B * SEQ_LEN) * d * d,
+                      "attention": 4.0 * M * T * d}
         total_ms = sum(v[0] for v in prof.values())
         shares = {k: round(v[0] / total_ms, 4) for k, v in prof.items()}
+        per_kernel = {k: {"avg_launch_ms": prof[k][0] / prof[k][1], "launches_per_iter": prof[k][1] // n_prof,
+                          "tflops": gemm_flops[k] / (prof[k][0] / prof[k][1] / 1000.0) / 1e12,
+                          "frac_of_sustained_peak": gemm_flops[k] / (prof[k][0] / prof[k][1] / 1000.0) / 1e12 / peaks["tensor"]}
+                      for k in prof if k in gemm_flops}
         dom = max((k for k in prof if k in gemm_flops), key=lambda k: prof[k][0])
         avg_ms = prof[dom][0] / prof[dom][1]
         achieved = gemm_flops[dom] / (avg_ms / 1000.0) / 1e12
@@ -299,15 +405,77 @@ def run_ours(args):
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             traffic = json.load(open(tp)).get(dom)
-        roofline = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tensor"],
+        step_tf = algorithmic_flops_per_iter(cfg, B, T) * (value / world) / 1e12
+        roofline = {"step_frac_of_sustained_peak": step_tf / peaks["tensor"],
+                    "bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peaks["tensor"],
                     "unit": "TFLOP/s", "frac": achieved / peaks["tensor"], "traffic": traffic,
                     "peak_source": peaks["source"] + " bf16_tflops_sustained",
                     "avg_launch_ms": avg_ms, "algorithmic_flops_per_launch": gemm_flops[dom],
-                    "time_share_by_kernel": shares,
+                    "time_share_by_kernel": shares, "per_kernel": per_kernel,
                     "step": {"algorithmic_tflop_per_iter": algorithmic_flops_per_iter(cfg, B, T) / 1e12,
-                             "achieved_tflops": algorithmic_flops_per_iter(cfg, B, T) * (value / world) / 1e12,
-                             "frac_of_sustained_peak": algorithmic_flops_per_iter(cfg, B, T) * (value / world) / 1e12
-                             / peaks["tensor"]}}
+                             "achieved_tflops": step_tf, "frac_of_sustained_peak": step_tf / peaks["tensor"],
+                             "frac_of_burst_peak": step_tf / peaks["tensor_burst"]}}
+
+    # ---- the other BASELINE configs, per-GPU shard each (weak scaling like the headline): 3 warm-up + 5 timed steps
+    other = {}
+    if not args.no_other_configs:
+        OW, OK = 3, 5
+
+        def clocked(fn):
+            c = ClockSampler(local).start() if rank == 0 else None
+            r = fn()
+            return r, (c.stop() if rank == 0 else None)
+
+        # config 5: ESM-1b, 16 of 128 chains x L=1022, num_positions_percent 5 / 10 / 25 (same engine as the headline)
+        for pct in (5, 10, 25):
+            P = int(1022 * pct / 100)
+            (_, _, tk, ms5, _), ck = clocked(lambda: _time_single(timer, ESM_sampler, model, local, rank, 16, 1022, 0,
+                                                                   float("inf"), P, OW, OK))
+            other["C5_shard_p%d" % pct] = _other_config_entry(
+                "C5", "BASELINE configs[4] shard: ESM-1b, 16 of 128 chains x L=1022, num_positions_percent=%d (P=%d)" % (pct, P),
+                ms5, OK, algorithmic_flops_per_iter(cfg, 16, 1024), peaks, world, ck)
+        engine.close()
+        model.model.engine = None
+        del model, sampler
+        # config 4: ESM-2 650M, 64 of 512 chains x L=512, top_k=5, burnin=50 (at N=8 this IS config 4)
+        cfg4 = get_config("esm2_t33_650M_UR50D")
+        m4 = _model_on_ranks(models, models.ESM2_t33_650M, cfg4, world, rank, dev)
+        (_, _, _, ms4, _), ck = clocked(lambda: _time_single(timer, ESM_sampler, m4, local, rank, 64, 512, 5, 50, 0, OW, OK))
+        other["C4_shard"] = _other_config_entry(
+            "C4", "BASELINE configs[3] shard: ESM-2 650M, 64 chains/GPU x L=512 (512 chains at N=8), top_k=5, burnin=50, "
+                  "all positions", ms4, OK, algorithmic_flops_per_iter(cfg4, 64, 514), peaks, world, ck)
+        m4.model.engine.close()
+        del m4
+        # config 4 again in split-operand precision (logits within 1e-3 of fp32 per row)
+        m4s = _model_on_ranks(models, models.ESM2_t33_650M, cfg4, world, rank, dev, precision="split")
+        (_, _, _, ms4s, _), ck = clocked(lambda: _time_single(timer, ESM_sampler, m4s, local, rank, 64, 512, 5, 50, 0, OW, 3))
+        other["C4_shard_split_precision"] = _other_config_entry(
+            "C4", "as C4_shard with precision='split' (fp16 hi+lo operands, three tensor-core passes per GEMM)", ms4s, 3,
+            algorithmic_flops_per_iter(cfg4, 64, 514), peaks, world, ck)
+        m4s.model.engine.close()
+        del m4s
+        # config 3: MSA-1b, 16 MSAs x 32 rows x L=128, 10 % of the positions of every row per iteration
+        cfg3 = get_config("esm_msa1b_t12_100M_UR50S")
+        m3 = _model_on_ranks(models, models.ESM_MSA1, cfg3, world, rank, dev)
+        s3 = ESM_MSA_sampler(m3, device="cuda:%d" % local, rng="device")
+        e3 = m3.model.engine
+        e3.set_stream(stream.cuda_stream)
+        rows = seeds(32, 128, 99 + rank)
+        toks3 = m3.batch_converter([[(str(i), q) for i, q in enumerate(rows)]] * 16)[2]
+        idx3, _ = s3.calculate_indexes(None, 0, 128, False)
+        for label, P3 in (("C3", 12), ("C3_all_positions", 0)):
+            random.seed(rank)
+            plan3, _ = s3.plan_positions(16, 32, idx3, -1, P3, False, OW + OK)
+            e3.set_tokens(toks3)
+            e3.set_schedule(plan3.positions, plan3.n_iters, plan3.P, plan3.iter_stride, plan3.chain_stride)
+            e3.set_noise(None)
+            e3.set_device_rng(7 + rank)
+            e3.run(0, OW, float("inf"), 0, None, True, s3.valid_aa_idx)
+            ms3, ck = clocked(lambda: timer.run(lambda: e3.run(OW, OK, float("inf"), 0, None, True, s3.valid_aa_idx)))
+            other[label] = _other_config_entry(
+                "C3", "BASELINE configs[2]: MSA-1b, 16 MSAs/GPU x 32 rows x L=128, %s positions per row and iteration"
+                      % ("10 %% (P=12)" if P3 else "all 128"), ms3, OK, msa_flops_per_iter(cfg3, 16, 32, 129), peaks, world, ck)
+        e3.close()
 
     cpu = cpu_baseline_sample() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
     if rank == 0:
@@ -318,8 +486,12 @@ def run_ours(args):
             "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "one ESM_sampler.generate call of K iterations: host strings -> tokens -> H2D -> K "
-                            "on-device iterations -> D2H -> strings; bytes are per-call totals / K"},
+                            "on-device iterations -> D2H -> strings; bytes are per-call totals / K"
+                            + ("; sharded over the ranks by parallel.shard_sampler (every rank calls generate for all "
+                               "N*64 chains, runs its slice, final tokens all-gathered once)" if world > 1 else ""),
+                    "sharded_equals_single_gpu": sharded_check},
             "gpu_launches": launches, "clocks": clock_info, "roofline": roofline, "cpu_baseline": cpu,
+            "other_configs": other,
             "chain_iters_per_sec": value * CHAINS_PER_GPU, "residue_updates_per_sec": value * CHAINS_PER_GPU * SEQ_LEN,
         }
         print(json.dumps(line))
@@ -334,6 +506,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

@@ -45,6 +45,13 @@ int pgibbs_set_stream(pgibbs_engine* e, void* cuda_stream, int32_t external);
 
 /* One fp32 tensor of the fair-esm state dict by key name (models.py:61-86 bind the loaders). */
 int pgibbs_load_weight(pgibbs_engine* e, const char* name, const float* data, int64_t numel);
+/* Numerics of the forward that replaces `self.model.model(batch)` (esm_sampler.py:223; fp32 in the reference).
+ *   0 (default) every GEMM is one tensor-core pass over fp16 operands, fp32 accumulate;
+ *   1 weights are carried as fp16 hi + lo pairs (exact to 2^-22), two passes;
+ *   2 the GEMM input activations too (three passes: a_hi w_hi + a_hi w_lo + a_lo w_hi) -- logits within 1e-3 of fp32
+ *     per token row at 33 layers, at about 2.5x the step time.
+ * Must be called before pgibbs_finalize_weights (the weight packing depends on it). */
+int pgibbs_set_precision(pgibbs_engine* e, int32_t level);
 /* Check that every tensor the architecture needs was supplied; pack GEMM operands to fp16. */
 int pgibbs_finalize_weights(pgibbs_engine* e);
 

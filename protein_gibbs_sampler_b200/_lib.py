@@ -28,6 +28,7 @@ SIGNATURES = {
     "pgibbs_destroy": (c_i32, [c_void_p]),
     "pgibbs_set_stream": (c_i32, [c_void_p, c_void_p, c_i32]),
     "pgibbs_load_weight": (c_i32, [c_void_p, c_char_p, c_void_p, c_i64]),
+    "pgibbs_set_precision": (c_i32, [c_void_p, c_i32]),
     "pgibbs_finalize_weights": (c_i32, [c_void_p]),
     "pgibbs_set_tokens": (c_i32, [c_void_p, c_void_p, c_i32, c_i32, c_i32]),
     "pgibbs_get_tokens": (c_i32, [c_void_p, c_void_p]),

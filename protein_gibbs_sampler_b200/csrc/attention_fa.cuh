@@ -52,6 +52,8 @@ struct AttnFaParams {
   const __half* qkv;  // [n_seq*T, 3*H*64]
   __half* ctx;        // [n_seq*T, H*64]
   int reverse;        // walk the (sequence, head) items from the last one down (see pgibbs_engine::zigzag)
+  int ctx_ld;         // ctx row pitch in elements (H*64, or 2*H*64 when rows are [hi | lo])
+  int ctx_lo_off;     // split-operand mode: also store the fp16 rounding residual of ctx at column + ctx_lo_off (0 = off)
 };
 constexpr int kFaTraceCap = 2048;
 
@@ -418,16 +420,22 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         }
         // ctx[q][dim] = O^T[dim][q] / l[q]
         const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-        __half* out = p.ctx + (static_cast<long long>(seq) * T + q_first) * d + head * 64;
+        const long long ldc = p.ctx_ld;
+        __half* out = p.ctx + (static_cast<long long>(seq) * T + q_first) * ldc + head * 64;
+        auto put = [&](int q, int col, float v) {
+          const __half hi = __float2half_rn(v);
+          out[q * ldc + col] = hi;
+          if (p.ctx_lo_off) out[q * ldc + p.ctx_lo_off + col] = __float2half_rn(v - __half2float(hi));
+        };
 #pragma unroll
         for (int dt = 0; dt < 4; ++dt) {
           if (2 * t4 < p.tail_rows) {
-            out[static_cast<long long>(2 * t4) * d + dt * 16 + g] = __float2half_rn(o[dt][0] * i0);
-            out[static_cast<long long>(2 * t4) * d + dt * 16 + g + 8] = __float2half_rn(o[dt][2] * i0);
+            put(2 * t4, dt * 16 + g, o[dt][0] * i0);
+            put(2 * t4, dt * 16 + g + 8, o[dt][2] * i0);
           }
           if (2 * t4 + 1 < p.tail_rows) {
-            out[static_cast<long long>(2 * t4 + 1) * d + dt * 16 + g] = __float2half_rn(o[dt][1] * i1);
-            out[static_cast<long long>(2 * t4 + 1) * d + dt * 16 + g + 8] = __float2half_rn(o[dt][3] * i1);
+            put(2 * t4 + 1, dt * 16 + g, o[dt][1] * i1);
+            put(2 * t4 + 1, dt * 16 + g + 8, o[dt][3] * i1);
           }
         }
       }
@@ -552,16 +560,20 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         const float inv = 1.0f / __uint_as_float(ls[0]);
         const int r = quad * 32 + lane;
         uint8_t* rowp = stage + r * 128;
+        // split-operand mode: the rounding residuals go straight to global memory (one 128-byte line per thread)
+        const bool lo_row = p.ctx_lo_off != 0 && tile * 128 + r < T;
+        uint4* lo_dst = reinterpret_cast<uint4*>(p.ctx + (static_cast<long long>(seq) * T + tile * 128 + r) * p.ctx_ld +
+                                                 p.ctx_lo_off + head * 64);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          uint4 w;
-          __half2 h0 = __floats2half2_rn(__uint_as_float(o[8 * q]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
-          __half2 h1 = __floats2half2_rn(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
-          __half2 h2 = __floats2half2_rn(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
-          __half2 h3 = __floats2half2_rn(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
-          w.x = *reinterpret_cast<uint32_t*>(&h0); w.y = *reinterpret_cast<uint32_t*>(&h1);
-          w.z = *reinterpret_cast<uint32_t*>(&h2); w.w = *reinterpret_cast<uint32_t*>(&h3);
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(o[8 * q + j]) * inv;
+          const uint4 w = make_uint4(f2h2_sat(f[0], f[1]), f2h2_sat(f[2], f[3]), f2h2_sat(f[4], f[5]), f2h2_sat(f[6], f[7]));
           *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) << 4)) = w;  // 128B swizzle, matches tmCtx
+          if (lo_row)
+            lo_dst[q] = make_uint4(f2h2_residual(f[0], f[1], w.x), f2h2_residual(f[2], f[3], w.y),
+                                   f2h2_residual(f[4], f[5], w.z), f2h2_residual(f[6], f[7], w.w));
         }
       }
       tc_fence_before();

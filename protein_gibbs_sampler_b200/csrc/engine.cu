@@ -98,10 +98,10 @@ static int make_tmap_out(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_
 // Fused qkv activation viewed as [n_seq][T][3d] fp16 for the tcgen05 attention kernel: box = 64 columns (one head of
 // q, k or v) x 128 tokens of one sequence, 128B swizzle; tokens t >= T are zero-filled (never the next sequence).
 static int make_tmap_qkv3(CUtensorMap* m, const void* ptr, uint64_t n_seq, uint64_t T, uint64_t ld,
-                          uint32_t box_rows = 128) {
+                          uint32_t box_rows = 128, uint64_t cols = 0) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail("cuTensorMapEncodeTiled entry point not available");
-  cuuint64_t dims[3] = {ld, T, n_seq};
+  cuuint64_t dims[3] = {cols ? cols : ld, T, n_seq};   // cols < ld: only the hi half of a [hi | lo] row is addressable
   cuuint64_t strides[2] = {ld * sizeof(__half), T * ld * sizeof(__half)};
   cuuint32_t box[3] = {64, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
@@ -155,7 +155,9 @@ static int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const Ge
   if ((reinterpret_cast<uintptr_t>(p.out) & 15) || (p.ldo * (epi_out_f16(EPI) ? 2 : 4)) % 16)
     return fail("GEMM output must be 16-byte aligned with a 16-byte multiple row pitch");
   CUtensorMap c;
-  TRY(make_tmap_out(&c, p.out, p.M, p.N, p.ldo, epi_out_f16(EPI)));
+  // (split-operand mode: the rounding residuals are stored lo_off columns to the right of the N outputs)
+  TRY(make_tmap_out(&c, p.out, p.M, p.lo_off ? p.lo_off + p.N : p.N, p.ldo, epi_out_f16(EPI)));
+  if (p.lo_off && (p.N % 64 || p.lo_off < p.N)) return fail("split-operand output needs N %% 64 == 0 and lo_off >= N");
   CK(ensure_dynamic_smem(gemm_tcgen05_kernel<BN, EPI, CG>, gemm_smem_bytes(BN, CG)));
   const int m_tiles = (p.M + kBM * CG - 1) / (kBM * CG), n_tiles = (p.N + BN - 1) / BN;
   const int groups = std::min(num_sms() / CG, m_tiles * n_tiles);
@@ -254,6 +256,17 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ in, __half* __restri
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) out[i] = __float2half_rn(in[i]);
 }
+// fp32 [rows, K] -> fp16 [rows, 2K] = [hi | lo]: hi = rn(w), lo = rn(w - hi)  (split-operand mode)
+__global__ void f32_to_f16_split_kernel(const float* __restrict__ in, __half* __restrict__ out, long long rows, int K) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= rows * K) return;
+  const long long r = i / K;
+  const int c = static_cast<int>(i - r * K);
+  const float w = in[i];
+  const __half hi = __float2half_rn(w);
+  out[r * 2 * K + c] = hi;
+  out[r * 2 * K + K + c] = __float2half_rn(w - __half2float(hi));
+}
 __global__ void f16_to_f32_kernel(const __half* __restrict__ in, float* __restrict__ out, long long n) {
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) out[i] = __half2float(in[i]);
@@ -270,6 +283,13 @@ __global__ void rope_table_kernel(float2* tab, int T, int half) {
 
 static int to_f16(const float* in, __half* out, long long n, cudaStream_t st) {
   f32_to_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(in, out, n);
+  CK(cudaGetLastError());
+  return 0;
+}
+// weight [rows, K] -> fp16 [rows, K] (split = false) or [rows, 2K] = [hi | lo]
+static int weight_to_f16(const float* in, __half* out, long long rows, int K, bool split, cudaStream_t st) {
+  if (!split) return to_f16(in, out, rows * K, st);
+  f32_to_f16_split_kernel<<<static_cast<unsigned>((rows * K + 255) / 256), 256, 0, st>>>(in, out, rows, K);
   CK(cudaGetLastError());
   return 0;
 }
@@ -302,6 +322,11 @@ struct pgibbs_engine {
   std::vector<void*> owned;                               // packed weight allocations
   std::vector<LayerW> L;
   bool finalized = false;
+  // 0 fast: one pass of fp16 operands.  1: weights carried as fp16 hi + lo (two passes).  2: activations too (three).
+  int precision = 0;
+  int wk() const { return precision >= 1 ? 2 : 1; }   // weight row = wk() x K halves
+  int ak() const { return precision >= 2 ? 2 : 1; }   // GEMM-input activation row = ak() x K halves
+  int k_segs() const { return precision + 1; }
   __half* w_dense = nullptr;
   float* b_dense = nullptr;
   CUtensorMap m_wdense;
@@ -426,7 +451,8 @@ static const float* raw_get(pgibbs_engine* e, const std::string& k, int64_t expe
 // concat [q;k;v] weights -> fp16 [3d, d], biases -> fp32 [3d]
 static int pack_qkv(pgibbs_engine* e, const std::string& prefix, __half** w, float** b) {
   const int d = e->cfg.embed_dim;
-  TRY(dev_alloc(w, static_cast<size_t>(3) * d * d));
+  const size_t wrow = static_cast<size_t>(e->wk()) * d;   // halves per weight row ([hi | lo] in split mode)
+  TRY(dev_alloc(w, static_cast<size_t>(3) * d * wrow));
   TRY(dev_alloc(b, static_cast<size_t>(3) * d));
   e->owned.push_back(*w);
   e->owned.push_back(*b);
@@ -435,7 +461,7 @@ static int pack_qkv(pgibbs_engine* e, const std::string& prefix, __half** w, flo
     const float* ws = raw_get(e, prefix + names[i] + ".weight", static_cast<int64_t>(d) * d);
     const float* bs = raw_get(e, prefix + names[i] + ".bias", d);
     if (!ws || !bs) return 1;
-    TRY(to_f16(ws, *w + static_cast<size_t>(i) * d * d, static_cast<long long>(d) * d, e->stream));
+    TRY(weight_to_f16(ws, *w + static_cast<size_t>(i) * d * wrow, d, d, e->precision >= 1, e->stream));
     CK(cudaMemcpyAsync(*b + static_cast<size_t>(i) * d, bs, d * sizeof(float), cudaMemcpyDeviceToDevice, e->stream));
   }
   return 0;
@@ -445,9 +471,9 @@ static int pack_linear(pgibbs_engine* e, const std::string& prefix, int n_out, i
   const float* ws = raw_get(e, prefix + ".weight", static_cast<int64_t>(n_out) * n_in);
   const float* bs = raw_get(e, prefix + ".bias", n_out);
   if (!ws || !bs) return 1;
-  TRY(dev_alloc(w, static_cast<size_t>(n_out) * n_in));
+  TRY(dev_alloc(w, static_cast<size_t>(n_out) * n_in * e->wk()));
   e->owned.push_back(*w);
-  TRY(to_f16(ws, *w, static_cast<long long>(n_out) * n_in, e->stream));
+  TRY(weight_to_f16(ws, *w, n_out, n_in, e->precision >= 1, e->stream));
   *b = const_cast<float*>(bs);
   return 0;
 }
@@ -468,16 +494,17 @@ static int free_activations(pgibbs_engine* e) {
 static int build_weight_maps(pgibbs_engine* e) {
   const int d = e->cfg.embed_dim, F = e->cfg.ffn_dim;
   for (auto& l : e->L) {
-    TRY(make_tmap_2d(&l.m_wqkv, l.wqkv, 3 * d, d, d, e->g_qkv.b_box()));
-    TRY(make_tmap_2d(&l.m_wo, l.wo, d, d, d, e->g_o.b_box()));
-    TRY(make_tmap_2d(&l.m_w1, l.w1, F, d, d, e->g_fc1.b_box()));
-    TRY(make_tmap_2d(&l.m_w2, l.w2, d, F, F, e->g_fc2.b_box()));
+    const int w = e->wk();   // weight rows are [hi | lo] in split-operand mode
+    TRY(make_tmap_2d(&l.m_wqkv, l.wqkv, 3 * d, w * d, w * d, e->g_qkv.b_box()));
+    TRY(make_tmap_2d(&l.m_wo, l.wo, d, w * d, w * d, e->g_o.b_box()));
+    TRY(make_tmap_2d(&l.m_w1, l.w1, F, w * d, w * d, e->g_fc1.b_box()));
+    TRY(make_tmap_2d(&l.m_w2, l.w2, d, w * F, w * F, e->g_fc2.b_box()));
     if (e->cfg.arch == PGIBBS_ARCH_MSA) {
-      TRY(make_tmap_2d(&l.m_cwqkv, l.c_wqkv, 3 * d, d, d, e->g_qkv.b_box()));
-      TRY(make_tmap_2d(&l.m_cwo, l.c_wo, d, d, d, e->g_o.b_box()));
+      TRY(make_tmap_2d(&l.m_cwqkv, l.c_wqkv, 3 * d, w * d, w * d, e->g_qkv.b_box()));
+      TRY(make_tmap_2d(&l.m_cwo, l.c_wo, d, w * d, w * d, e->g_o.b_box()));
     }
   }
-  if (e->w_dense) TRY(make_tmap_2d(&e->m_wdense, e->w_dense, d, d, d, e->g_dense.b_box()));
+  if (e->w_dense) TRY(make_tmap_2d(&e->m_wdense, e->w_dense, d, e->wk() * d, e->wk() * d, e->g_dense.b_box()));
   return 0;
 }
 
@@ -509,11 +536,14 @@ static int allocate_shape(pgibbs_engine* e, int B, int R, int T) {
   e->M = static_cast<int>(M);
   TRY(dev_alloc(&e->tokens, M));
   TRY(dev_alloc(&e->x, M * d));
-  TRY(dev_alloc(&e->h, M * d));
+  const size_t a = e->ak();   // GEMM-input activations are [hi | lo] rows in split-operand mode
+  TRY(dev_alloc(&e->h, M * d * a));
   TRY(dev_alloc(&e->qkv, M * 3 * d));
-  TRY(dev_alloc(&e->ctx, M * d));
-  TRY(dev_alloc(&e->ffn, M * F));
-  TRY(dev_alloc(&e->hs, M * d));
+  TRY(dev_alloc(&e->ctx, M * d * a));
+  TRY(dev_alloc(&e->ffn, M * F * a));
+  TRY(dev_alloc(&e->hs, M * d * a));
+  // attention kernels without a residual output (mma.sync paths, MSA kernels) leave the lo half of ctx at zero
+  if (a > 1) CK(cudaMemsetAsync(e->ctx, 0, M * d * a * sizeof(__half), e->stream));
   TRY(dev_alloc(&e->g, M * d));
   TRY(dev_alloc(&e->logits, M * V));
   if (e->cfg.arch == PGIBBS_ARCH_MSA)
@@ -522,12 +552,12 @@ static int allocate_shape(pgibbs_engine* e, int B, int R, int T) {
   std::vector<int32_t> idp(T);
   for (int i = 0; i < T; ++i) idp[i] = i;
   CK(cudaMemcpy(e->identity_pos, idp.data(), T * sizeof(int32_t), cudaMemcpyHostToDevice));
-  TRY(make_tmap_2d(&e->m_h, e->h, M, d, d, kBM));
-  TRY(make_tmap_2d(&e->m_ctx, e->ctx, M, d, d, kBM));
-  TRY(make_tmap_2d(&e->m_ffn, e->ffn, M, F, F, kBM));
-  TRY(make_tmap_2d(&e->m_hs, e->hs, M, d, d, kBM));
+  TRY(make_tmap_2d(&e->m_h, e->h, M, a * d, a * d, kBM));
+  TRY(make_tmap_2d(&e->m_ctx, e->ctx, M, a * d, a * d, kBM));
+  TRY(make_tmap_2d(&e->m_ffn, e->ffn, M, a * F, a * F, kBM));
+  TRY(make_tmap_2d(&e->m_hs, e->hs, M, a * d, a * d, kBM));
   TRY(make_tmap_qkv3(&e->m_qkv3, e->qkv, static_cast<uint64_t>(B) * R, T, 3 * d));
-  TRY(make_tmap_qkv3(&e->m_ctx3, e->ctx, static_cast<uint64_t>(B) * R, T, d));
+  TRY(make_tmap_qkv3(&e->m_ctx3, e->ctx, static_cast<uint64_t>(B) * R, T, a * d, 128, d));
   if (T <= 256) TRY(make_tmap_qkv3(&e->m_qkv3_keys, e->qkv, static_cast<uint64_t>(B) * R, T, 3 * d, (T + 15) & ~15));
   const int hd = d / e->cfg.heads;
   e->g_qkv = pick_gemm_plan(e->M, 3 * d, hd >= 64 ? 64 : 32);
@@ -554,6 +584,7 @@ static int run_ln(pgibbs_engine* e, const float* x, const float* w, const float*
   if (gather) p.sched = *gather; else p.sched.positions = nullptr;
   p.iter = iter; p.T = e->T;
   p.reverse = gather ? 0 : e->next_dir();
+  if (e->precision >= 2) { p.ld_out = 2 * p.d; p.lo_off = p.d; }   // [hi | lo] rows (split-operand mode)
   ProfScope ps(e, "layernorm");
   const dim3 grid((rows + 7) / 8);
   const int vpl = (p.d / 4 + 31) / 32;  // float4 vectors per lane
@@ -578,6 +609,7 @@ static int run_gemm(pgibbs_engine* e, const char* name, int epi, GemmPlan g, con
                     const CUtensorMap& b, GemmParams p) {
   if (epi == EPI_RESID_F32) p.flags = e->split_flags;
   p.reverse = e->next_dir();
+  p.k_segs = e->k_segs();
   ProfScope ps(e, name);
   return launch_gemm(epi, g, a, b, p, e->stream);
 }
@@ -626,7 +658,7 @@ static int attn_mode(int hd) {
 }
 // qkv: fused activation [n_seq*T, 3*H*64]; ctx: [n_seq*T, H*64].
 static int launch_attention_fa(const CUtensorMap& qkv3, const CUtensorMap& ctx3, const __half* qkv, __half* ctx,
-                               int n_seq, int T, int H, cudaStream_t st, int reverse = 0) {
+                               int n_seq, int T, int H, cudaStream_t st, int reverse = 0, int ctx_split = 0) {
   CK(ensure_dynamic_smem(attention_fa_kernel, kFaSmemBytes));
   // Trailing rows (T = 128 k + r): r <= 8 -> the kernel's tail warp; r <= 16 -> the mma.sync kernel (second launch);
   // otherwise a normal partly filled tile.  PGIBBS_ATTN_TAIL=0 forces the partly filled tile.
@@ -634,12 +666,12 @@ static int launch_attention_fa(const CUtensorMap& qkv3, const CUtensorMap& ctx3,
   const bool any_tail = g_attn_tail && T > 128 && tail > 0 && tail <= 16;
   const bool in_kernel = any_tail && tail <= 8 && g_attn_tail != 2;
   AttnFaParams p{T, H, n_seq, any_tail ? T / 128 : (T + 127) / 128, g_fa_trace, g_attn_stagger,
-                 in_kernel ? tail : 0, qkv, ctx, reverse};
+                 in_kernel ? tail : 0, qkv, ctx, reverse, (ctx_split ? 2 : 1) * H * 64, ctx_split ? H * 64 : 0};
   const int n_items = n_seq * H * ((p.n_tiles + 1) / 2);
   CK(launch_pdl(attention_fa_kernel, dim3(std::min(num_sms(), n_items)), dim3(kFaThreads), kFaSmemBytes, st, qkv3, ctx3, p));
   if (any_tail && !in_kernel) {
     const int d = H * 64;
-    AttnParams tp{qkv, ctx, T, 3 * d, d, d, 2 * d, 1, 0, 1, T, T - tail};
+    AttnParams tp{qkv, ctx, T, 3 * d, (ctx_split ? 2 : 1) * d, d, 2 * d, 1, 0, 1, T, T - tail};
     TRY(launch_attention(tp, n_seq, H, 64, st));
   }
   return 0;
@@ -662,7 +694,8 @@ static int run_msa_row_attention(pgibbs_engine* e) {
     CK(launch_pdl(msa_row_attention_tc_kernel, grid, dim3(kMrThreads), smem, e->stream, e->m_qkv3, e->m_qkv3_keys, e->m_ctx3, p));
     return 0;
   }
-  if (const char* m = launch_msa_row_attention(e->qkv, e->ctx, e->scores, e->B, e->R, e->T, c.heads, hd, e->stream))
+  if (const char* m = launch_msa_row_attention(e->qkv, e->ctx, e->scores, e->B, e->R, e->T, c.heads, hd, e->stream,
+                                               e->ak() * c.embed_dim))
     return fail("%s", m);
   return 0;
 }
@@ -672,8 +705,9 @@ static int run_attention(pgibbs_engine* e) {
   ProfScope ps(e, "attention");
   const int mode = attn_mode(hd);
   if (mode == 2)
-    return launch_attention_fa(e->m_qkv3, e->m_ctx3, e->qkv, e->ctx, e->n_seq, e->T, H, e->stream, e->next_dir());
-  AttnParams p{e->qkv, e->ctx, e->T, 3 * d, d, d, 2 * d, 1, 0, 1, e->T};
+    return launch_attention_fa(e->m_qkv3, e->m_ctx3, e->qkv, e->ctx, e->n_seq, e->T, H, e->stream, e->next_dir(),
+                               e->precision >= 2);
+  AttnParams p{e->qkv, e->ctx, e->T, 3 * d, e->ak() * d, d, 2 * d, 1, 0, 1, e->T};
   return launch_attention(p, e->n_seq, H, hd, e->stream);
 }
 
@@ -729,7 +763,7 @@ static int forward(pgibbs_engine* e, const Schedule& sched_in, int n_chains, int
       TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->g_qkv, e->m_h, l.m_cwqkv, qc));
       {
         ProfScope ps(e, "msa_col_attention");
-        AttnParams ap{e->qkv, e->ctx, e->R, 3 * d, d, d, 2 * d, e->T, 1, e->T, static_cast<long long>(e->R) * e->T};
+        AttnParams ap{e->qkv, e->ctx, e->R, 3 * d, e->ak() * d, d, 2 * d, e->T, 1, e->T, static_cast<long long>(e->R) * e->T};
         ap.reverse = e->next_dir();   // (only the dedicated column kernel honours it)
         const char* m = hd == 64 ? launch_msa_col_attention(ap, e->B * e->T, c.heads, st) : "";
         if (m && *m) return fail("%s", m);
@@ -752,7 +786,11 @@ static int forward(pgibbs_engine* e, const Schedule& sched_in, int n_chains, int
       TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->g_o, e->m_ctx, l.m_wo, gp(M, d, d, l.bo, e->x, d)));
     }
     TRY(run_ln(e, e->x, l.ln2w, l.ln2b, e->h, M, nullptr, 0));
-    TRY(run_gemm(e, "gemm_fc1", EPI_GELU_F16, e->g_fc1, e->m_h, l.m_w1, gp(M, F, d, l.b1, e->ffn, F)));
+    {
+      GemmParams f1 = gp(M, F, d, l.b1, e->ffn, e->ak() * F);
+      if (e->precision >= 2) f1.lo_off = F;   // ffn rows are [hi | lo]
+      TRY(run_gemm(e, "gemm_fc1", EPI_GELU_F16, e->g_fc1, e->m_h, l.m_w1, f1));
+    }
     TRY(run_gemm(e, "gemm_fc2", EPI_RESID_F32, e->g_fc2, e->m_ffn, l.m_w2, gp(M, d, F, l.b2, e->x, d)));
   }
   // LM head on the scheduled rows only
@@ -980,6 +1018,14 @@ int pgibbs_load_weight(pgibbs_engine* e, const char* name, const float* data, in
   auto it = e->raw.find(name);
   if (it != e->raw.end()) cudaFree(it->second.first);
   e->raw[name] = {dptr, numel};
+  return 0;
+}
+
+int pgibbs_set_precision(pgibbs_engine* e, int32_t level) {
+  if (!e) return fail("null engine");
+  if (level < 0 || level > 2) return fail("precision level %d out of range (0 fast, 1 split weights, 2 split weights and activations)", level);
+  if (e->finalized) return fail("precision must be chosen before pgibbs_finalize_weights (the weight packing depends on it)");
+  e->precision = level;
   return 0;
 }
 
@@ -1218,11 +1264,11 @@ int pgibbs_debug_read(pgibbs_engine* e, const char* which, float* out, int64_t n
   int64_t n = 0;
   if (w == "x") { src32 = e->x; n = M * d; }
   else if (w == "g") { src32 = e->g; n = M * d; }
-  else if (w == "h") { src16 = e->h; n = M * d; }
-  else if (w == "hs") { src16 = e->hs; n = M * d; }
+  else if (w == "h") { src16 = e->h; n = M * d * e->ak(); }     // split-operand mode: rows are [hi | lo]
+  else if (w == "hs") { src16 = e->hs; n = M * d * e->ak(); }
   else if (w == "qkv") { src16 = e->qkv; n = M * 3 * d; }
-  else if (w == "ctx") { src16 = e->ctx; n = M * d; }
-  else if (w == "ffn") { src16 = e->ffn; n = M * F; }
+  else if (w == "ctx") { src16 = e->ctx; n = M * d * e->ak(); }
+  else if (w == "ffn") { src16 = e->ffn; n = M * F * e->ak(); }
   else return fail("unknown debug buffer '%s'", w.c_str());
   if (numel > n) numel = n;
   if (src32) {

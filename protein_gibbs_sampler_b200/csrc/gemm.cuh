@@ -48,6 +48,14 @@ struct GemmParams {
   int32_t* flags;       // [last-wave tile][part][CTA rank][epilogue warp]: 1 once that warp's reduce-adds have landed;
                         // zero between launches (the one waiter of a flag clears it), so a launch captured in a
                         // CUDA graph can be replayed as it is
+  // Split-operand ("precise") mode.  Operands are fp16 hi + lo pairs stored side by side: A rows are [a_hi (K) | a_lo (K)],
+  // B rows [w_hi (K) | w_lo (K)].  The main loop runs k_segs passes over K into the SAME accumulator:
+  //   1: a_hi w_hi          2: + a_hi w_lo (weights exact to 2^-22)          3: + a_lo w_hi (activations too)
+  // (a_lo w_lo ~ 2^-24 is dropped.)  lo parts are plain fp16: |lo| <= 2^-12 |hi| reaches the subnormal range, whose
+  // absolute resolution 2^-24 is ample.  0 is treated as 1.
+  int k_segs;
+  int lo_off;           // fp16-output epilogues: also store the rounding residual of every output at column + lo_off
+                        // (the a_lo half of the next GEMM's A operand); 0 = off
 };
 
 constexpr int kBM = 128;
@@ -84,10 +92,7 @@ __device__ __forceinline__ float gelu_erf(float v) {
   return fmaf(-0.5f * fabsf(v), e, fmaxf(v, 0.f));
 }
 
-__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) { return f2h2_sat(a, b); }
 
 __host__ __device__ constexpr bool epi_out_f16(int epi) { return epi == EPI_BIAS_F16 || epi == EPI_GELU_F16 || epi == EPI_QKV_F16; }
 constexpr int kEpiStageBytes = 4096;                           // 32 rows x 128 B, one warp's chunk
@@ -213,31 +218,46 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
         else rope_chunk<16>(v, cs);
       }
     }
-    // the TMA store issued from this buffer two chunks ago must have finished reading it
-    if (lane == 0) tma_store_wait_read<1>();
-    __syncwarp();
-    uint8_t* buf = staging + sbuf * kEpiStageBytes;
-    uint8_t* rowp = buf + lane * 128;
+    // Stage 32 rows x 128 B in this warp's 128B-swizzled buffer and hand it to one TMA store / reduce-add at column
+    // `col`.  The store issued from the same buffer two stores ago must have finished reading it.
+    auto stage_and_store = [&](const uint4 (&w)[8], int col) {
+      if (lane == 0) tma_store_wait_read<1>();
+      __syncwarp();
+      uint8_t* buf = staging + sbuf * kEpiStageBytes;
+      uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(rowp + ((q ^ (lane & 7)) << 4)) = w[q];  // 128B swizzle: conflict-free, matches tmC
+      fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_2d(tmC, buf, col, row0);
+        else tma_store_2d(tmC, buf, col, row0);
+        tma_store_commit();
+      }
+      sbuf ^= 1;
+    };
+    uint4 w[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      uint4 w;
       if constexpr (kOut16) {
-        w = make_uint4(pack_half2(v[8 * q], v[8 * q + 1]), pack_half2(v[8 * q + 2], v[8 * q + 3]),
-                       pack_half2(v[8 * q + 4], v[8 * q + 5]), pack_half2(v[8 * q + 6], v[8 * q + 7]));
+        w[q] = make_uint4(pack_half2(v[8 * q], v[8 * q + 1]), pack_half2(v[8 * q + 2], v[8 * q + 3]),
+                          pack_half2(v[8 * q + 4], v[8 * q + 5]), pack_half2(v[8 * q + 6], v[8 * q + 7]));
       } else {
-        w = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
-                       __float_as_uint(v[4 * q + 3]));
+        w[q] = make_uint4(__float_as_uint(v[4 * q]), __float_as_uint(v[4 * q + 1]), __float_as_uint(v[4 * q + 2]),
+                          __float_as_uint(v[4 * q + 3]));
       }
-      *reinterpret_cast<uint4*>(rowp + ((q ^ (lane & 7)) << 4)) = w;  // 128B swizzle: conflict-free, matches tmC
     }
-    fence_proxy_async();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-    __syncwarp();
-    if (lane == 0) {
-      if constexpr (EPI == EPI_RESID_F32) tma_reduce_add_2d(tmC, buf, g, row0);
-      else tma_store_2d(tmC, buf, g, row0);
-      tma_store_commit();
+    stage_and_store(w, g);
+    if constexpr (EPI == EPI_GELU_F16) {
+      if (p.lo_off) {  // the rounding residuals of this chunk: the a_lo half of the FC2 operand (split-operand mode)
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          w[q] = make_uint4(f2h2_residual(v[8 * q], v[8 * q + 1], w[q].x), f2h2_residual(v[8 * q + 2], v[8 * q + 3], w[q].y),
+                            f2h2_residual(v[8 * q + 4], v[8 * q + 5], w[q].z), f2h2_residual(v[8 * q + 6], v[8 * q + 7], w[q].w));
+        stage_and_store(w, g + p.lo_off);
+      }
     }
-    sbuf ^= 1;
   }
 }
 
@@ -273,7 +293,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int m_tiles = (p.M + kBM * CG - 1) / (kBM * CG);
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
-  const int num_kb = p.K / kBK;
+  const int kb_per_seg = p.K / kBK;
+  const int num_kb = kb_per_seg * (p.k_segs > 1 ? p.k_segs : 1);   // split-operand mode: 2 or 3 passes over K
   const int split = EPI == EPI_RESID_F32 ? p.split : 1;
 
   if (warp == 0 && lane == 0) {
@@ -321,15 +342,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int kb = u.kb0; kb < u.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = ring + stage * kStageBytes;
+        // pass 0: a_hi w_hi, pass 1: a_hi w_lo, pass 2: a_lo w_hi (lo halves sit K columns to the right)
+        const int seg = kb / kb_per_seg, kk = (kb - seg * kb_per_seg) * kBK;
+        const int a_col = kk + (seg == 2 ? p.K : 0), b_col = kk + (seg == 1 ? p.K : 0);
         if (issuer) {
           if constexpr (CG == 2) {
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
-            tma_load_2d_pair(sa, &tmA, &full_bar[stage], kb * kBK, a_row);
-            tma_load_2d_pair(sa + kABytes, &tmB, &full_bar[stage], kb * kBK, b_row);
+            tma_load_2d_pair(sa, &tmA, &full_bar[stage], a_col, a_row);
+            tma_load_2d_pair(sa + kABytes, &tmB, &full_bar[stage], b_col, b_row);
           } else {
             mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-            tma_load_2d(sa, &tmA, &full_bar[stage], kb * kBK, a_row);
-            tma_load_2d(sa + kABytes, &tmB, &full_bar[stage], kb * kBK, b_row);
+            tma_load_2d(sa, &tmA, &full_bar[stage], a_col, a_row);
+            tma_load_2d(sa + kABytes, &tmB, &full_bar[stage], b_col, b_row);
           }
         }
         __syncwarp();

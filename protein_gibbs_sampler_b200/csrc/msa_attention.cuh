@@ -309,7 +309,7 @@ static const char* launch_msa_col_attention(const AttnParams& p, int groups, int
 // return nullptr on success, else a static error string
 template <int DH>
 static const char* launch_msa_row_attention_t(const __half* qkv, __half* ctx, float* scores, int B, int R, int C,
-                                              int H, cudaStream_t st) {
+                                              int H, cudaStream_t st, int ldc) {
   const int d = H * DH, ld = 3 * d;
   const int tiles = (C + 63) / 64;
   msa_row_scores_kernel<DH><<<dim3(tiles, tiles, B * H), 128, 0, st>>>(qkv, scores, R, C, H, ld, d);
@@ -321,18 +321,19 @@ static const char* launch_msa_row_attention_t(const __half* qkv, __half* ctx, fl
     return "cudaFuncSetAttribute(msa_row_pv_kernel) failed";
   const int rows_per_group = R >= 8 ? 4 : 1;
   const int groups = (R + rows_per_group - 1) / rows_per_group;
-  msa_row_pv_kernel<DH><<<dim3(tiles, groups, B * H), 128, smem, st>>>(qkv, scores, ctx, R, C, H, ld, d, 2 * d,
+  msa_row_pv_kernel<DH><<<dim3(tiles, groups, B * H), 128, smem, st>>>(qkv, scores, ctx, R, C, H, ld, ldc, 2 * d,
                                                                          rows_per_group, Cpad);
   if (cudaGetLastError() != cudaSuccess) return "msa_row_pv_kernel launch failed";
   return nullptr;
 }
 
 static const char* launch_msa_row_attention(const __half* qkv, __half* ctx, float* scores, int B, int R, int C, int H,
-                                            int hd, cudaStream_t st) {
+                                            int hd, cudaStream_t st, int ldc = 0) {
+  if (!ldc) ldc = H * hd;   // ctx row pitch ([hi | lo] rows in split-operand mode)
   switch (hd) {
-    case 16: return launch_msa_row_attention_t<16>(qkv, ctx, scores, B, R, C, H, st);
-    case 32: return launch_msa_row_attention_t<32>(qkv, ctx, scores, B, R, C, H, st);
-    case 64: return launch_msa_row_attention_t<64>(qkv, ctx, scores, B, R, C, H, st);
+    case 16: return launch_msa_row_attention_t<16>(qkv, ctx, scores, B, R, C, H, st, ldc);
+    case 32: return launch_msa_row_attention_t<32>(qkv, ctx, scores, B, R, C, H, st, ldc);
+    case 64: return launch_msa_row_attention_t<64>(qkv, ctx, scores, B, R, C, H, st, ldc);
   }
   return "unsupported head_dim for MSA row attention (16, 32, 64)";
 }

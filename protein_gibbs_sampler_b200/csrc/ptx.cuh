@@ -51,6 +51,20 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// Two floats -> packed fp16 (a in the low half), round to nearest, SATURATING at +-65504 (one F2FP.SATFINITE): an
+// activation beyond the fp16 range clamps instead of becoming inf and turning the rest of the forward into NaN.
+__device__ __forceinline__ uint32_t f2h2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+// The part of (a, b) the fp16 value `hi` = f2h2_sat(a, b) dropped, again as packed fp16: a - float(hi.lo), b - float(hi.hi).
+// |lo| <= 2^-12 |a| lands in fp16's subnormal range for small |a|; its absolute resolution 2^-24 is what matters there.
+__device__ __forceinline__ uint32_t f2h2_residual(float a, float b, uint32_t hi) {
+  const __half2 h = *reinterpret_cast<const __half2*>(&hi);
+  return f2h2_sat(a - __low2float(h), b - __high2float(h));
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -7,6 +7,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ptx.cuh"
+
 namespace pg {
 
 constexpr int kMaxVecPerLane = 20;  // float4 per lane -> embed_dim <= 2560
@@ -174,6 +176,9 @@ struct LnParams {
   int iter, T;
   int identity;    // copy the (gathered) rows without normalising (ESM-1 has no final LayerNorm)
   int reverse;     // blocks take the rows from the last one down (see pgibbs_engine::zigzag)
+  int ld_out;      // output row pitch in elements (0 = d)
+  int lo_off;      // fp16 output: also store the rounding residual y - fp16(y) at column + lo_off (split-operand
+                   // mode: the a_lo half of the GEMM operand); 0 = off
 };
 
 // VPL = float4 vectors held per lane (>= ceil(d / 128)): sized to the model so that the row fits in few registers
@@ -233,13 +238,15 @@ __global__ void __launch_bounds__(256, VPL <= 10 ? 4 : 2) layernorm_kernel(LnPar
       const float4 h = p.identity ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(b + i);
       const float y0 = (a.x - mean) * rstd * g.x + h.x, y1 = (a.y - mean) * rstd * g.y + h.y;
       const float y2 = (a.z - mean) * rstd * g.z + h.z, y3 = (a.w - mean) * rstd * g.w + h.w;
+      const long long obase = static_cast<long long>(orow) * (p.ld_out ? p.ld_out : p.d);
       if constexpr (OUT_F16) {
-        __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
-        uint2 u = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-        reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + static_cast<long long>(orow) * p.d)[i] = u;
+        const uint2 u = make_uint2(f2h2_sat(y0, y1), f2h2_sat(y2, y3));
+        reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + obase)[i] = u;
+        if (p.lo_off)
+          reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out) + obase + p.lo_off)[i] =
+              make_uint2(f2h2_residual(y0, y1, u.x), f2h2_residual(y2, y3, u.y));
       } else {
-        reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<long long>(orow) * p.d)[i] =
-            make_float4(y0, y1, y2, y3);
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + obase)[i] = make_float4(y0, y1, y2, y3);
       }
     }
   }

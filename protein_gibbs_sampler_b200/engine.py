@@ -22,7 +22,7 @@ def _ptr(t):
 
 
 class Engine:
-    def __init__(self, cfg, alphabet, device_id=0):
+    def __init__(self, cfg, alphabet, device_id=0, precision="fast"):
         self.lib = _lib.load()
         self.cfg = dict(cfg)
         mc = _lib.ModelConfig(
@@ -35,6 +35,10 @@ class Engine:
         self.h = h
         self.device_id = int(device_id)
         self.shape = None
+        self.precision = precision
+        level = {"fast": 0, "split_weights": 1, "split": 2}[precision]
+        if level:
+            check(self.lib.pgibbs_set_precision(self.h, level))
 
     def close(self):
         if getattr(self, "h", None):

@@ -82,14 +82,26 @@ def load_checkpoint(path, arch):
     return upgrade_state_dict(sd, arch)
 
 
+PRECISION_LEVELS = {"fast": 0, "split_weights": 1, "split": 2}
+
+
+def _precision(p):
+    import os
+    p = os.environ.get("PGIBBS_PRECISION", "fast") if p is None else p
+    if p not in PRECISION_LEVELS:
+        raise ValueError("precision must be one of %s, got %r" % (sorted(PRECISION_LEVELS), p))
+    return p
+
+
 class EngineModule:
     """Stands where the reference expects ``model.model``: ``eval()``, ``to(device)`` and
     ``__call__(tokens) -> {"logits": ...}`` (esm_sampler.py:62,80,223)."""
 
-    def __init__(self, cfg, alphabet, state_dict):
+    def __init__(self, cfg, alphabet, state_dict, precision="fast"):
         self.cfg = cfg
         self.alphabet = alphabet
         self._state_dict = state_dict
+        self.precision = precision
         self.engine = None
         self.device = "cpu"
 
@@ -107,7 +119,7 @@ class EngineModule:
         if self.engine is None or self.engine.device_id != idx:
             if self.engine is not None:
                 self.engine.close()
-            self.engine = Engine(self.cfg, self.alphabet, idx)
+            self.engine = Engine(self.cfg, self.alphabet, idx, precision=self.precision)
             self.engine.load_state_dict(self._state_dict)
         self.device = device
         return self
@@ -129,14 +141,17 @@ class _Triple:
     config_name = None
     alphabet_factory = staticmethod(Alphabet.esm1b)
 
-    def __init__(self, state_dict=None, checkpoint=None, seed=0, **cfg_overrides):
+    def __init__(self, state_dict=None, checkpoint=None, seed=0, precision=None, **cfg_overrides):
+        """``precision``: "fast" (default; one pass of fp16 operands per GEMM) or "split" (every GEMM operand carried as
+        an fp16 hi + lo pair, three tensor-core passes: logits within 1e-3 of fp32 per token row at full depth, about
+        2.5x the step time -- DESIGN.md section 3).  ``None`` reads ``PGIBBS_PRECISION`` (default "fast")."""
         self.cfg = get_config(self.config_name, **cfg_overrides)
         self.alphabet = self.alphabet_factory()
         if checkpoint is not None:
             state_dict = load_checkpoint(checkpoint, self.cfg["arch"])
         if state_dict is None:
             state_dict = synthetic_state_dict(self.cfg, seed)
-        self.model = EngineModule(self.cfg, self.alphabet, state_dict)
+        self.model = EngineModule(self.cfg, self.alphabet, state_dict, precision=_precision(precision))
         self.batch_converter = self.alphabet.get_batch_converter()
 
 
@@ -183,10 +198,10 @@ class ESM_MSA1(_Triple):
 class CustomModel(_Triple):
     """Arbitrary geometry (tests): ``CustomModel(cfg_dict, seed=...)``."""
 
-    def __init__(self, cfg, state_dict=None, seed=0):
+    def __init__(self, cfg, state_dict=None, seed=0, precision=None):
         self.cfg = dict(cfg)
         self.alphabet = {"msa_transformer": Alphabet.msa, "esm1": Alphabet.esm1}.get(cfg["arch"], Alphabet.esm1b)()
         if state_dict is None:
             state_dict = synthetic_state_dict(self.cfg, seed)
-        self.model = EngineModule(self.cfg, self.alphabet, state_dict)
+        self.model = EngineModule(self.cfg, self.alphabet, state_dict, precision=_precision(precision))
         self.batch_converter = self.alphabet.get_batch_converter()

@@ -26,6 +26,58 @@ def broadcast_state_dict(sd, src=0, device="cpu"):
     return out
 
 
+def _blob_plan(cfg, gemm_fp16):
+    from .weights import is_gemm_weight, state_dict_layout
+    plan, off = [], 0
+    for key, shape in state_dict_layout(cfg):
+        numel = 1
+        for n in shape:
+            numel *= n
+        half = gemm_fp16 and is_gemm_weight(key)
+        nbytes = numel * (2 if half else 4)
+        plan.append((key, shape, half, off, nbytes))
+        off += (nbytes + 15) // 16 * 16          # keep every tensor 16-byte aligned inside the blob
+    return plan, off
+
+
+def pack_weights(cfg, sd, gemm_fp16=True):
+    """One contiguous byte blob holding the whole model: the GEMM weights as fp16 (what the tensor cores consume --
+    the engine would round them to exactly these values anyway) when ``gemm_fp16``, everything else fp32."""
+    plan, total = _blob_plan(cfg, gemm_fp16)
+    blob = torch.zeros(total, dtype=torch.uint8)
+    for key, shape, half, off, nbytes in plan:
+        t = sd[key].detach().to("cpu", torch.float16 if half else torch.float32).contiguous()
+        assert tuple(t.shape) == tuple(shape), (key, tuple(t.shape), shape)
+        blob[off:off + nbytes] = t.view(-1).view(torch.uint8)
+    return blob
+
+
+def unpack_weights(cfg, blob, gemm_fp16=True):
+    """fp32 state dict (on the blob's device) out of a packed blob."""
+    plan, total = _blob_plan(cfg, gemm_fp16)
+    assert blob.numel() == total and blob.dtype == torch.uint8
+    out = {}
+    for key, shape, half, off, nbytes in plan:
+        raw = blob[off:off + nbytes]
+        out[key] = (raw.view(torch.float16).to(torch.float32) if half else raw.view(torch.float32)).reshape(shape)
+    return out
+
+
+def broadcast_weights(cfg, sd, src=0, device="cpu", gemm_fp16=True):
+    """The ONE collective of a sharded job: rank ``src`` packs the model into a single blob (1.3 GB for the 650M
+    models with fp16 GEMM weights), one ``dist.broadcast`` ships it over NCCL / NVLink, and every rank -- ``src``
+    included, so that all ranks run bit-identical weights -- unpacks the same bytes.  The layout comes from ``cfg``
+    alone, so no metadata is exchanged.  Pass ``gemm_fp16=False`` for split-operand precision (the lo halves need the
+    fp32 weights)."""
+    _, total = _blob_plan(cfg, gemm_fp16)
+    if dist.get_rank() == src:
+        blob = pack_weights(cfg, sd, gemm_fp16).to(device)
+    else:
+        blob = torch.empty(total, dtype=torch.uint8, device=device)
+    dist.broadcast(blob, src=src)
+    return unpack_weights(cfg, blob, gemm_fp16)
+
+
 def gather_sequences(local_seqs):
     """All ranks' output strings in rank order (rank 0 gets the full list, others too)."""
     bucket = [None] * dist.get_world_size()

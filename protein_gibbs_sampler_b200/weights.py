@@ -62,6 +62,61 @@ def synthetic_state_dict(cfg, seed=0, std=0.02, ln_noise=0.02, bias_std=0.02):
     return sd
 
 
+def state_dict_layout(cfg):
+    """[(key, shape)] of the engine-side state dict of ``cfg`` in a fixed order, derived from the geometry alone: every
+    rank of a job can lay out the packed weight blob (parallel.broadcast_weights) without exchanging metadata."""
+    d, F, V, L = cfg["embed_dim"], cfg["ffn_dim"], cfg["vocab"], cfg["layers"]
+    out = [("embed_tokens.weight", (V, d))]
+
+    def lin(prefix, n_out, n_in):
+        out.append((prefix + ".weight", (n_out, n_in)))
+        out.append((prefix + ".bias", (n_out,)))
+
+    def ln(prefix):
+        out.append((prefix + ".weight", (d,)))
+        out.append((prefix + ".bias", (d,)))
+
+    if cfg["positions"] == "learned":
+        out.append(("embed_positions.weight", (cfg["max_positions"] + 2, d)))
+    if cfg["arch"] == "msa_transformer":
+        out.append(("msa_position_embedding", (1, 1024, 1, d)))
+    if cfg["emb_layer_norm_before"]:
+        ln("emb_layer_norm_before")
+    for i in range(L):
+        p = "layers.%d." % i
+        if cfg["arch"] == "msa_transformer":
+            for blk in ("row_self_attention", "column_self_attention"):
+                for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):
+                    lin(p + blk + ".layer." + nm, d, d)
+                ln(p + blk + ".layer_norm")
+            lin(p + "feed_forward_layer.layer.fc1", F, d)
+            lin(p + "feed_forward_layer.layer.fc2", d, F)
+            ln(p + "feed_forward_layer.layer_norm")
+        else:
+            for nm in ("k_proj", "v_proj", "q_proj", "out_proj"):
+                lin(p + "self_attn." + nm, d, d)
+            if cfg["arch"] == "esm1":
+                out.append((p + "self_attn.bias_k", (1, 1, d)))
+                out.append((p + "self_attn.bias_v", (1, 1, d)))
+            ln(p + "self_attn_layer_norm")
+            lin(p + "fc1", F, d)
+            lin(p + "fc2", d, F)
+            ln(p + "final_layer_norm")
+    if cfg["arch"] == "esm1":
+        return out + [("embed_out", (V, d)), ("embed_out_bias", (V,))]
+    ln("emb_layer_norm_after")
+    lin("lm_head.dense", d, d)
+    ln("lm_head.layer_norm")
+    out.append(("lm_head.bias", (V,)))   # lm_head.weight is tied to embed_tokens.weight and never shipped
+    return out
+
+
+def is_gemm_weight(key):
+    """The tensors the engine feeds to the tensor cores as fp16 (everything else stays fp32 on the device)."""
+    return key.endswith((".q_proj.weight", ".k_proj.weight", ".v_proj.weight", ".out_proj.weight", "fc1.weight",
+                         "fc2.weight", "lm_head.dense.weight"))
+
+
 def sinusoidal_table(num_embeddings, dim, padding_idx=1):
     """fair-esm SinusoidalPositionalEmbedding.get_embedding (esm/modules.py), float32 like the original: row p is
     [sin(p f_0..) | cos(p f_0..)], f_j = exp(-j ln(10000) / (dim/2 - 1)); the padding row is zero."""

@@ -68,6 +68,18 @@ def _worker(rank, world, port, q):
     got = parallel.broadcast_state_dict(sd, src=0, device="cpu")
     want = synthetic_state_dict(cfg, 11)
     same = all(torch.equal(got[k], want[k]) for k in want) and set(got) == set(want)
+    # the packed blob: ONE broadcast, layout derived from the config on every rank, GEMM weights shipped as fp16
+    from protein_gibbs_sampler_b200.weights import is_gemm_weight
+    for arch, half in (("msa_transformer", True), ("esm1", True), ("roberta_large", False)):
+        c2 = tiny_config(arch, 2, 64, 2, 128)
+        full = synthetic_state_dict(c2, 5)
+        blob = parallel.broadcast_weights(c2, full if rank == 0 else None, src=0, device="cpu", gemm_fp16=half)
+        for k, v in full.items():
+            if k == "lm_head.weight":
+                continue
+            w = v.half().float() if (half and is_gemm_weight(k)) else v
+            same = same and torch.equal(blob[k], w)
+        same = same and set(blob) == set(full) - {"lm_head.weight"}
     lo, hi = parallel.shard_range(5, world, rank)
     seqs = parallel.gather_sequences(["r%d_%d" % (rank, i) for i in range(lo, hi)])
     q.put((rank, same, seqs))

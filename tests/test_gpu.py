@@ -19,18 +19,36 @@ def rel(got, want):
     return ((got - want).abs().max() / want.abs().max()).item()
 
 
+def rel_rows(got, want, valid_ids=None):
+    """SURVEY 8c's stricter metric: every token row on its own, max|delta| / max|logit| of THAT row (the batch-wide
+    maximum in `rel` is dominated by the rows with the largest logits); with `valid_ids`, numerator and denominator
+    run over the candidate residues only (what generate_step reads).  Returns the worst row."""
+    g, w = got.reshape(-1, got.shape[-1]), want.reshape(-1, want.shape[-1])
+    if valid_ids is not None:
+        g, w = g[:, valid_ids], w[:, valid_ids]
+    return ((g - w).abs().amax(-1) / w.abs().amax(-1)).max().item()
+
+
+# Documented bound of the single-pass fp16-operand ("fast") mode on the per-row metric at full depth (33 layers):
+# CPU emulation of the operand rounding gives 1.4-2.2e-3 over weight / token seeds (tests/tools/precision_study3.py).
+ROW_TOL_FAST = 2.5e-3
+# ... and on the batch-wide metric: 0.6-1.0e-3 (ESM-1b), 0.9-1.6e-3 (ESM-2 650M) in the same emulation; measured on
+# the B200 at the BASELINE shapes 1.0e-3 (config 2) and 1.0-1.3e-3 (config 4).  Split-operand mode asserts 1e-3.
+BATCH_TOL_FAST_DEEP = 1.7e-3
+
+
 @pytest.fixture(scope="module", autouse=True)
 def _need_gpu(gpu_lib):
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"
 
 
-def make(cfg, seed, rng="replay"):
+def make(cfg, seed, rng="replay", precision="fast"):
     from protein_gibbs_sampler_b200 import models
     from protein_gibbs_sampler_b200.esm_msa_sampler import ESM_MSA_sampler
     from protein_gibbs_sampler_b200.esm_sampler import ESM_sampler
     from protein_gibbs_sampler_b200.weights import synthetic_state_dict
     sd = synthetic_state_dict(cfg, seed)
-    m = models.CustomModel(cfg, state_dict=sd)
+    m = models.CustomModel(cfg, state_dict=sd, precision=precision)
     cls = ESM_MSA_sampler if cfg["arch"] == "msa_transformer" else ESM_sampler
     return cls(m, device="cuda:0", rng=rng), sd
 
@@ -71,6 +89,27 @@ def test_gemm_operator(M, N, K, bn):
     assert rel(op_gemm(A, B, bias, C=C0, epilogue=2, block_n=bn), want + C0) < 2e-5
 
 
+def test_gemm_operator_config2_rows_vs_torch():
+    """The GEMM shapes of BASELINE config 2 (M = 64 x 258 = 16512 token rows: 65 row blocks, partly filled last wave)
+    against torch on the same fp16-rounded operands: out-projection (residual epilogue) and FC1 (GELU epilogue)."""
+    from protein_gibbs_sampler_b200.engine import op_gemm
+    g = torch.Generator().manual_seed(16512)
+    M = 16512
+    for N, K, epi in [(1280, 1280, 2), (5120, 1280, 4), (1280, 5120, 2)]:
+        A, B, bias = torch.randn(M, K, generator=g) * 0.5, torch.randn(N, K, generator=g) * 0.05, torch.randn(N, generator=g)
+        want = A.half().float() @ B.half().float().t() + bias
+        if epi == 2:
+            C0 = torch.randn(M, N, generator=g)
+            got = op_gemm(A, B, bias, C=C0, epilogue=2)
+            want = want + C0
+        else:
+            got = op_gemm(A, B, bias, epilogue=4)
+            want = torch.nn.functional.gelu(want)
+        assert rel(got, want) < 2e-5, (N, K, epi, rel(got, want))
+        # every row block was written (the last, partly filled 256-row tile included)
+        assert rel(got[-300:], want[-300:]) < 2e-5 and rel(got[:300], want[:300]) < 2e-5
+
+
 @pytest.mark.parametrize("n_seq,T,H,Dh", [(2, 64, 2, 64), (2, 27, 20, 16), (3, 258, 4, 64), (2, 130, 3, 32),
                                           (1, 1024, 2, 64), (3, 5, 2, 64)])
 def test_attention_operator(n_seq, T, H, Dh):
@@ -88,7 +127,7 @@ def test_sampler_tail_bit_exact_vs_oracle():
     g = torch.Generator().manual_seed(0)
     for valid, top_k, temp in [(list(range(4, 24)), 0, None), (list(range(4, 24)), 3, None),
                                (list(range(4, 24)) + [30], 5, 0.7), ([3, 5, 1], 2, None), (list(range(4, 24)), 1, 2.0),
-                               (list(range(4, 24)), 50, None)]:
+                               (list(range(4, 24)), 50, None), (list(range(4, 24)), 4, -1.5)]:
         rows = 3000
         logits = torch.randn(rows, 33, generator=g) * 2
         noise = torch.empty(rows, len(valid)).exponential_(1, generator=g)
@@ -139,7 +178,7 @@ def _tokens(cfg, shape, seed):
     return tok
 
 
-@pytest.mark.parametrize("arch,layers,d,H,F,shape", [
+FORWARD_CASES = [
     ("esm2", 2, 128, 2, 256, (2, 24)), ("roberta_large", 2, 128, 2, 256, (2, 24)),
     ("esm2", 6, 320, 20, 1280, (2, 27)),                    # BASELINE config 1 geometry (esm2_t6_8M)
     ("roberta_large", 3, 256, 4, 512, (3, 130)), ("esm2", 2, 640, 20, 2560, (2, 70)),
@@ -157,27 +196,124 @@ def _tokens(cfg, shape, seed):
     ("msa_transformer", 2, 128, 2, 256, (1, 40, 12)),       # more than 32 rows: generic column-attention kernel
     ("msa_transformer", 2, 192, 3, 256, (1, 20, 19)),       # odd head count: generic column-attention kernel
     ("msa_transformer", 12, 768, 12, 3072, (1, 6, 40)),     # full-depth MSA-1b (config 3 model)
-])
-def test_forward_logits_vs_oracle(arch, layers, d, H, F, shape):
+    # ---- full depth AT the BASELINE token shapes (every perf number is quoted on these)
+    ("roberta_large", 33, 1280, 20, 5120, (2, 258)),        # config 2: L = 256
+    ("roberta_large", 33, 1280, 20, 5120, (1, 1024)),       # config 5: L = 1022, the longest the positions allow
+    ("esm2", 33, 1280, 20, 5120, (2, 514)),                 # config 4: L = 512
+    ("msa_transformer", 12, 768, 12, 3072, (1, 32, 129)),   # config 3: 32 rows x L = 128
+]
+
+
+def _forward_errors(arch, layers, d, H, F, shape, precision="fast", weights_seed=3):
     from oracle.fair_esm import OracleModel
     from protein_gibbs_sampler_b200.config import tiny_config
     cfg = tiny_config(arch, layers, d, H, F)
-    s, sd = make(cfg, 3)
+    s, sd = make(cfg, weights_seed, precision=precision)
     tok = _tokens(cfg, shape, 5)
     got = s.model.model(tok)["logits"]
     want = OracleModel(cfg, sd).model(tok)["logits"]
-    assert got.shape == want.shape
+    assert got.shape == want.shape and bool(torch.isfinite(got).all())
     rms = ((got - want).pow(2).mean().sqrt() / want.abs().max()).item()
-    print("forward %s L%d d%d %s: max|d|/max|logit| = %.3e, rms|d|/max|logit| = %.3e" % (arch, layers, d, shape,
-                                                                                       rel(got, want), rms))
-    assert rms < 0.5 * LOGIT_TOL
-    if (arch, layers, d) == ("esm2", 33, 1280):
-        # Single-pass fp16 operands bound the worst element of the deepest rotary model at 0.9-1.2e-3 of the
-        # largest logit whatever the input (CPU emulation of the operand rounding: tests/tools/precision_study2.py,
-        # DESIGN.md section 3); the rms error is 3e-4.  Every other geometry sits below 1e-3 with margin.
-        assert rel(got, want) < 1.5 * LOGIT_TOL
-    else:
-        assert rel(got, want) < LOGIT_TOL
+    errs = dict(batch=rel(got, want), rms=rms, row=rel_rows(got, want), row_valid=rel_rows(got, want, s.valid_aa_idx))
+    print("forward[%s] %s L%d d%d %s: batch max %.3e  rms %.3e  worst row %.3e  worst row over valid ids %.3e"
+          % (precision, arch, layers, d, shape, errs["batch"], rms, errs["row"], errs["row_valid"]))
+    return errs
+
+
+@pytest.mark.parametrize("arch,layers,d,H,F,shape", FORWARD_CASES)
+def test_forward_logits_vs_oracle(arch, layers, d, H, F, shape):
+    """Default ("fast") numerics: one pass of fp16 operands on the tensor cores, fp32 everywhere else.
+    Tolerances -- north_star's 1e-3, measured two ways: over the batch (max|d| / max|logit|) and per token row (SURVEY
+    8c).  Models of up to 12 layers (MSA-1b included) are inside it.  The 33-layer models sit AT the single-pass limit
+    (DESIGN.md section 3): only the documented single-pass bounds are asserted for them here, and the 1e-3 tolerance
+    itself is asserted in split-operand mode (test_forward_logits_precise_mode)."""
+    e = _forward_errors(arch, layers, d, H, F, shape)
+    assert e["rms"] < 0.5 * LOGIT_TOL
+    if layers < 30:
+        assert e["batch"] < LOGIT_TOL and e["row"] < 2 * LOGIT_TOL
+    else:   # 33 layers, single pass: AT the tolerance, not inside it (BASELINE.md section 2 says so)
+        assert e["batch"] < BATCH_TOL_FAST_DEEP and e["row"] < ROW_TOL_FAST
+
+
+@pytest.mark.parametrize("arch,layers,d,H,F,shape", [
+    ("roberta_large", 33, 1280, 20, 5120, (2, 66)), ("esm2", 33, 1280, 20, 5120, (2, 40)),
+    ("roberta_large", 33, 1280, 20, 5120, (2, 258)), ("esm2", 33, 1280, 20, 5120, (2, 514)),     # configs 2 and 4
+    ("msa_transformer", 12, 768, 12, 3072, (1, 6, 40)), ("esm1", 6, 768, 12, 3072, (2, 66)),
+    ("esm2", 6, 320, 20, 1280, (2, 27)), ("msa_transformer", 2, 128, 4, 256, (1, 3, 70)),
+])
+def test_forward_logits_precise_mode(arch, layers, d, H, F, shape):
+    """Split-operand mode (`precision="split"`, pgibbs_set_precision level 2): every GEMM runs
+    a_hi w_hi + a_hi w_lo + a_lo w_hi on fp16 hi / lo pairs, so only the attention-internal roundings (q, k, v, P in
+    fp16) remain.  north_star's 1e-3 holds per token row as well as over the batch for the 33-layer models, ESM-2 650M
+    included -- the tolerance the single-pass mode cannot reach at that depth (CPU emulation: precision_study3.py)."""
+    e = _forward_errors(arch, layers, d, H, F, shape, precision="split")
+    assert e["batch"] < LOGIT_TOL and e["row"] < LOGIT_TOL and e["rms"] < 0.25 * LOGIT_TOL
+
+
+def test_precision_levels_order_and_agree():
+    """fast -> split_weights -> split: the error against the fp32 oracle shrinks level by level on the same inputs,
+    and every level samples from the same chain state machinery (one generate runs in each mode)."""
+    cfg_args = ("roberta_large", 12, 512, 8, 2048, (2, 130))
+    errs = {pr: _forward_errors(*cfg_args, precision=pr) for pr in ("fast", "split_weights", "split")}
+    assert errs["split"]["rms"] < 0.6 * errs["split_weights"]["rms"] and errs["split_weights"]["rms"] < 0.85 * errs["fast"]["rms"]
+    from protein_gibbs_sampler_b200.config import tiny_config
+    cfg = tiny_config("esm2", 2, 128, 2, 256)
+    outs = {}
+    for pr in ("fast", "split"):
+        s, _ = make(cfg, 7, precision=pr)
+        random.seed(11); torch.manual_seed(11)
+        outs[pr] = s.generate(3, "MKTAYIAKQRQISFVKSHFSRQ", batch_size=3, num_iters=17, top_k=3, burnin=2, num_positions=5,
+                              show_progress_bar=False)
+        assert len(outs[pr]) == 3 and all(len(x) == 22 for x in outs[pr])
+    same = sum(a == b for x, y in zip(outs["fast"], outs["split"]) for a, b in zip(x, y))
+    assert same >= 0.8 * 66   # same noise, logits 1e-3 apart: nearly every draw agrees
+
+
+def test_forward_outlier_weights_stay_finite_and_in_tolerance():
+    """Real ESM checkpoints carry a few residual-stream channels and FFN units far above the rest; synthetic
+    N(0, 0.02) weights never exercise the dynamic range of `h` / `qkv` / `ffn`.  Here four residual channels are fed
+    by FC2 / out-projection rows scaled x60 and eight FC1 units are scaled x100 in four of six layers: the residual
+    stream reaches the hundreds and the FFN activations the tens (fp16 range: 65504).
+      * Logits stay finite in every mode.
+      * Single-pass fp16 operands lose accuracy here, as any 16-bit inference does: after LayerNorm the outlier
+        channels are ~300x the rest, and their 2^-12 relative rounding is an absolute error comparable to the SIGNAL
+        of the small channels.  Documented bound: 1e-2 of the largest logit (measured 3.6e-3).
+      * Split-operand mode carries every GEMM operand as hi + lo (22 bits); what remains is the fp16 rounding of
+        q / k / v and P inside the attention, amplified by the same outliers: 2e-3 documented (measured 1.1e-3).
+      * Beyond the fp16 range the engine saturates (cvt.satfinite) instead of producing inf / NaN."""
+    from oracle.fair_esm import OracleModel
+    from protein_gibbs_sampler_b200 import models
+    from protein_gibbs_sampler_b200.config import tiny_config
+    from protein_gibbs_sampler_b200.esm_sampler import ESM_sampler
+    from protein_gibbs_sampler_b200.weights import synthetic_state_dict
+    for arch in ("roberta_large", "esm2"):
+        cfg = tiny_config(arch, 6, 320, 5, 1280)
+        sd = synthetic_state_dict(cfg, 9)
+        chans, units = [5, 77, 130, 301], list(range(40, 48))
+        for li in (1, 3, 4, 5):
+            sd["layers.%d.fc2.weight" % li][chans] *= 60.0
+            sd["layers.%d.self_attn.out_proj.weight" % li][chans] *= 60.0
+            sd["layers.%d.fc1.weight" % li][units] *= 100.0
+            sd["layers.%d.fc1.bias" % li][units] *= 100.0
+        tok = _tokens(cfg, (2, 70), 5)
+        want = OracleModel(cfg, sd).model(tok)["logits"]
+        for precision, tol in (("fast", 1e-2), ("split", 2 * LOGIT_TOL)):
+            s = ESM_sampler(models.CustomModel(cfg, state_dict=sd, precision=precision), device="cuda:0")
+            got = s.model.model(tok)["logits"]
+            eng = s.model.model.engine
+            pitch = 2 if precision == "split" else 1      # split mode: ffn rows are [hi | lo]
+            x = eng.debug_read("x", tok.numel() * 320)
+            ffn = eng.debug_read("ffn", tok.numel() * 1280 * pitch).view(tok.numel(), pitch, 1280)[:, 0]
+            print("outliers %s [%s]: max|x| %.0f max|ffn| %.0f  batch %.3e row %.3e" % (
+                arch, precision, x.abs().max(), ffn.abs().max(), rel(got, want), rel_rows(got, want)))
+            assert x.abs().max() > 100 and ffn.abs().max() > 10        # the outliers are really there
+            assert bool(torch.isfinite(got).all())
+            assert rel(got, want) < tol, (arch, precision, rel(got, want))
+        # beyond the fp16 range: saturate, never inf / NaN
+        sd2 = {k: v.clone() for k, v in sd.items()}
+        sd2["layers.2.fc1.weight"][units] *= 1.0e5
+        s2 = ESM_sampler(models.CustomModel(cfg, state_dict=sd2), device="cuda:0")
+        assert bool(torch.isfinite(s2.model.model(tok)["logits"]).all())
 
 
 # ------------------------------------------------------------------------------------------ end to end
@@ -204,6 +340,90 @@ def test_generate_reproduces_reference_golden(golden):
         s, sd = make(c["cfg"], c["weights_seed"])
         exact += s.generate(**c["kwargs"]) == c["output"]
     assert exact >= len(golden["cases"]) - 1
+
+
+def _check_trace(sampler, oracle, case, n_rows_per_unit):
+    """One golden case, iteration by iteration FROM THE REFERENCE'S OWN STATE: the token tensor the reference fed to
+    forward number f (`states[f]`, already masked) is loaded into the engine, the reference's target positions of that
+    iteration and the Exp(1) variates it consumed there are replayed, and ONE iteration runs on the device.  Then
+      (1) every sampled residue equals the oracle's sampler tail applied to the ENGINE's logits of that state -- the
+          device tail is bit-exact given its logits -- and the untouched positions are unchanged;
+      (2) the engine's logits are within tolerance of the oracle's;
+      (3) the oracle's tail on the ORACLE's logits reproduces the reference's next state (the trace is understood);
+    so a residue that differs from the reference's can only come from a logit difference inside the tolerance band.
+    Returns (residues sampled, residues that differ from the reference)."""
+    from oracle.sampler_tail import generate_step_with_noise
+    from protein_gibbs_sampler_b200.esm_sampler import draw_replay_noise, _effective_k
+    kw = case["kwargs"]
+    eng = sampler.model.model.require_engine()
+    valid = sampler.valid_aa_idx
+    num_iters, top_k, burnin = kw["num_iters"], kw.get("top_k", 0), kw.get("burnin", float("inf"))
+    temperature = kw.get("temperature")
+    states, targets = case["states"], case["targets"]
+    if not targets:   # mask=False runs never call the (traced) masking hook: num_positions=0 -> every candidate position
+        assert not kw.get("mask", True) and not kw.get("num_positions") and not kw.get("leader_length")
+        T = torch.tensor(states[0]).shape[-1]
+        L = T - 2 if n_rows_per_unit == 1 else T - 1          # <cls> seq <eos>  /  MSA rows: <cls> seq
+        every = list(range(1, L + 1))
+        targets = [[([every] * n_rows_per_unit if n_rows_per_unit > 1 else every) for _ in st] for st in states]
+    assert len(states) == len(targets) and len(states) % num_iters == 0
+    random.seed(case["rng_seed"]); torch.manual_seed(case["rng_seed"])
+    sampled = differ = 0
+    for f, (state, tg) in enumerate(zip(states, targets)):
+        it = f % num_iters
+        tok = torch.tensor(state)
+        flat_t = [t for unit in tg for t in (unit if n_rows_per_unit > 1 else [unit])]   # per chain (MSA: per row)
+        n_chains, P = len(flat_t), len(flat_t[0])
+        assert n_chains == tok.numel() // tok.shape[-1]
+        if it == 0:   # the reference draws from torch's generator residue by residue; one pre-draw per outer batch
+            noise, stride = draw_replay_noise(num_iters, n_chains * P, len(valid), top_k, burnin)
+        pos = torch.tensor(flat_t, dtype=torch.int32).reshape(1, n_chains, P)
+        eng.set_tokens(tok)
+        eng.set_schedule(pos.numpy(), 1, P, n_chains * P, P, False)
+        eng.set_noise(noise[it:it + 1].contiguous(), stride)
+        eng.set_chain_offset(0)
+        eng.run(0, 1, float("inf") if it < burnin else 0, top_k, temperature, False, valid)
+        got = eng.get_tokens().reshape(n_chains, -1)
+        logits_e = eng.forward_logits(tok).reshape(n_chains, tok.shape[-1], -1)
+        logits_o = oracle.model(tok)["logits"].reshape(n_chains, tok.shape[-1], -1)
+        assert rel(logits_e, logits_o) < LOGIT_TOL
+        before = tok.reshape(n_chains, -1)
+        touched = torch.zeros_like(before, dtype=torch.bool)
+        # the reference's next state: states[f+1] outside its own freshly masked targets, or the final output
+        last = it == num_iters - 1
+        nxt = None if last else torch.tensor(states[f + 1]).reshape(n_chains, -1)
+        nxt_masked = set() if last or not kw.get("mask", True) else \
+            {(c, p) for c, ps in enumerate(t for unit in targets[f + 1] for t in (unit if n_rows_per_unit > 1 else [unit]))
+             for p in ps}
+        k = _effective_k(top_k, len(valid), it < burnin)
+        for c in range(n_chains):
+            for j, p in enumerate(flat_t[c]):
+                touched[c, p] = True
+                nz = noise[it, c * P + j]
+                mine = generate_step_with_noise(logits_e[c, p], nz, valid, k, temperature)
+                assert int(got[c, p]) == mine, (f, c, p)                                   # (1)
+                ref_tok = generate_step_with_noise(logits_o[c, p], nz, valid, k, temperature)
+                if nxt is not None and (c, p) not in nxt_masked and flat_t[c].count(p) == 1:
+                    assert int(nxt[c, p]) == ref_tok, (f, c, p)                            # (3)
+                sampled += 1
+                differ += mine != ref_tok
+        assert torch.equal(got[~touched], before[~touched])                               # (1) untouched positions
+    return sampled, differ
+
+
+def test_generate_traces_iteration_by_iteration(golden):
+    """The `states` / `targets` traces of the reference runs (tests/golden/make_golden.py), replayed one iteration at a
+    time from the reference's own state, single-sequence and MSA samplers."""
+    from oracle.fair_esm import OracleModel
+    total = wrong = 0
+    for c in golden["cases"] + golden["msa_cases"]:
+        s, sd = make(c["cfg"], c["weights_seed"])
+        msa = c["cfg"]["arch"] == "msa_transformer"
+        n, d = _check_trace(s, OracleModel(c["cfg"], sd), c, len(c["kwargs"]["seed_msa"]) if msa else 1)
+        total += n
+        wrong += d
+    print("trace replay: %d residues sampled, %d differ from the reference (each inside the logit error band)" % (total, wrong))
+    assert total > 400 and wrong <= 0.02 * total
 
 
 def test_msa_generate_reproduces_reference_golden(golden):
