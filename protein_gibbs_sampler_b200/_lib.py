@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpgibbs.so")
+# (PGIBBS_LIB_PATH: A/B tooling only -- e.g. profiling a previous build of the same ABI)
+LIB_PATH = os.environ.get("PGIBBS_LIB_PATH") or os.path.join(_HERE, "libpgibbs.so")
 
 c_i32, c_i64, c_f32 = ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 c_void_p, c_char_p = ctypes.c_void_p, ctypes.c_char_p

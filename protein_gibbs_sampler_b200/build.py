@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libpgibbs.so")
+OUT = os.environ.get("PGIBBS_LIB_OUT") or os.path.join(HERE, "libpgibbs.so")   # (override: A/B builds for tooling)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--shared", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
