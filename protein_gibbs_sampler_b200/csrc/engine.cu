@@ -126,7 +126,7 @@ static int num_sms() {
 // A GEMM's tiling: tile width and whether a CTA pair (cta_group::2, 256-row tiles) computes it.
 // The B tensor map's box holds bn / cg rows.
 constexpr int kSplitFlagInts = 4096;  // K-split flags: >= 148 groups x 2 ranks x 8 epilogue warps
-static int g_gemm_split = 1;
+static int g_gemm_split = 0;              // PGIBBS_GEMM_SPLIT=1: last-wave K-split of the residual GEMMs (off: it makes a chain's low-order bits depend on the batch it runs in)
 static int g_pdl = 1;                 // PGIBBS_PDL=0: plain stream-ordered launches
 static int g_graph = 1;               // PGIBBS_GRAPH=0: every iteration is launched kernel by kernel
 static int g_zigzag = 1;              // PGIBBS_ZIGZAG=0: every kernel walks its rows in ascending order
