@@ -296,14 +296,29 @@ def _time_single(timer, sampler_cls, model, local, rank, B, L, top_k, burnin, nu
     eng.run(0, W, burnin, top_k, None, True, s.valid_aa_idx)
     launches0 = eng.launch_count()
     ms = timer.run(lambda: eng.run(W, K, burnin, top_k, None, True, s.valid_aa_idx), profiler)
-    return s, plan, toks, ms, eng.launch_count() - launches0
+    launches = eng.launch_count() - launches0
+    _time_single.kernels = _kernel_shares(eng, lambda: eng.run(W + K - 1, 1, burnin, top_k, None, True, s.valid_aa_idx)) \
+        if (rank == 0 and not profiler) else None
+    return s, plan, toks, ms, launches
 
 
-def _other_config_entry(name, workload, ms, K, flops, peaks, world, clock):
+def _kernel_shares(engine, run_one):
+    """Share of the step per kernel class: one extra iteration with CUDA events around every launch (rank 0)."""
+    engine.profile_enable(True)
+    run_one()
+    engine.sync()
+    prof = engine.profile_read()
+    engine.profile_enable(False)
+    total = sum(v[0] for v in prof.values()) or 1.0
+    return {k: {"share": round(v[0] / total, 4), "avg_launch_us": round(1000.0 * v[0] / v[1], 2), "launches": v[1]}
+            for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+
+
+def _other_config_entry(name, workload, ms, K, flops, peaks, world, clock, kernels=None):
     tf = flops / (ms / K / 1000.0) / 1e12
     return {"workload": workload, "steps": K, "ms_per_step": ms / K, "iters_per_sec": world * K / (ms / 1000.0),
             "n_gpus": world, "algorithmic_tflop_per_iter_per_gpu": flops / 1e12, "achieved_tflops_per_gpu": tf,
-            "frac_of_sustained_peak": tf / peaks["tensor"], "clocks": clock}
+            "frac_of_sustained_peak": tf / peaks["tensor"], "clocks": clock, "kernels": kernels}
 
 
 def run_ours(args):
@@ -433,7 +448,7 @@ def run_ours(args):
                                                                    float("inf"), P, OW, OK))
             other["C5_shard_p%d" % pct] = _other_config_entry(
                 "C5", "BASELINE configs[4] shard: ESM-1b, 16 of 128 chains x L=1022, num_positions_percent=%d (P=%d)" % (pct, P),
-                ms5, OK, algorithmic_flops_per_iter(cfg, 16, 1024), peaks, world, ck)
+                ms5, OK, algorithmic_flops_per_iter(cfg, 16, 1024), peaks, world, ck, _time_single.kernels)
         engine.close()
         model.model.engine = None
         del model, sampler
@@ -443,7 +458,7 @@ def run_ours(args):
         (_, _, _, ms4, _), ck = clocked(lambda: _time_single(timer, ESM_sampler, m4, local, rank, 64, 512, 5, 50, 0, OW, OK))
         other["C4_shard"] = _other_config_entry(
             "C4", "BASELINE configs[3] shard: ESM-2 650M, 64 chains/GPU x L=512 (512 chains at N=8), top_k=5, burnin=50, "
-                  "all positions", ms4, OK, algorithmic_flops_per_iter(cfg4, 64, 514), peaks, world, ck)
+                  "all positions", ms4, OK, algorithmic_flops_per_iter(cfg4, 64, 514), peaks, world, ck, _time_single.kernels)
         m4.model.engine.close()
         del m4
         # config 4 again in split-operand precision (logits within 1e-3 of fp32 per row)
@@ -451,7 +466,7 @@ def run_ours(args):
         (_, _, _, ms4s, _), ck = clocked(lambda: _time_single(timer, ESM_sampler, m4s, local, rank, 64, 512, 5, 50, 0, OW, 3))
         other["C4_shard_split_precision"] = _other_config_entry(
             "C4", "as C4_shard with precision='split' (fp16 hi+lo operands, three tensor-core passes per GEMM)", ms4s, 3,
-            algorithmic_flops_per_iter(cfg4, 64, 514), peaks, world, ck)
+            algorithmic_flops_per_iter(cfg4, 64, 514), peaks, world, ck, _time_single.kernels)
         m4s.model.engine.close()
         del m4s
         # config 3: MSA-1b, 16 MSAs x 32 rows x L=128, 10 % of the positions of every row per iteration
@@ -472,9 +487,10 @@ def run_ours(args):
             e3.set_device_rng(7 + rank)
             e3.run(0, OW, float("inf"), 0, None, True, s3.valid_aa_idx)
             ms3, ck = clocked(lambda: timer.run(lambda: e3.run(OW, OK, float("inf"), 0, None, True, s3.valid_aa_idx)))
+            k3 = _kernel_shares(e3, lambda: e3.run(OW + OK - 1, 1, float("inf"), 0, None, True, s3.valid_aa_idx)) if rank == 0 else None
             other[label] = _other_config_entry(
                 "C3", "BASELINE configs[2]: MSA-1b, 16 MSAs/GPU x 32 rows x L=128, %s positions per row and iteration"
-                      % ("10 %% (P=12)" if P3 else "all 128"), ms3, OK, msa_flops_per_iter(cfg3, 16, 32, 129), peaks, world, ck)
+                      % ("10 %% (P=12)" if P3 else "all 128"), ms3, OK, msa_flops_per_iter(cfg3, 16, 32, 129), peaks, world, ck, k3)
         e3.close()
 
     cpu = cpu_baseline_sample() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
