@@ -148,3 +148,40 @@ def test_msa_generate_reproduces_reference(golden):
 def test_partition_golden(golden):
     for c in golden["fixtures"]["partition"]:
         assert gibbs_loop.partition(list(range(c["n"])), c["k"]) == c["out"]
+
+
+# ------------------------------------------------------------------ second witness for the MSA / ESM-1 forwards
+@pytest.mark.parametrize("shape,row_chunk,col_chunk", [((2, 4, 11), 3, 5), ((1, 1, 9), 1, 2), ((1, 7, 14), 2, 14), ((1, 5, 6), 8, 1)])
+def test_msa_oracle_agrees_with_independent_witness(shape, row_chunk, col_chunk):
+    """oracle/fair_esm.MSAOracle (batched float32 tensor algebra) against oracle/witness.msa_forward (numpy float64,
+    explicit loops over MSA / head / row / column, tied-row scores accumulated row chunk by row chunk and columns
+    walked in chunks, as fair-esm does above max_tokens_per_msa): two restatements written in different styles from the
+    same published algorithm must agree to float32 rounding -- the pin for a forward no third-party port exists for."""
+    import numpy as np
+    from oracle.fair_esm import OracleModel
+    from oracle.witness import msa_forward
+    cfg = tiny_config("msa_transformer", 2, 48, 3, 96)
+    sd = synthetic_state_dict(cfg, 13)
+    g = torch.Generator().manual_seed(shape[-1])
+    tok = torch.randint(4, 24, shape, generator=g)
+    tok[..., 0] = 0
+    tok[0, 0, 2:4] = 32
+    tok[0, -1, 1] = 30
+    got = OracleModel(cfg, sd).model(tok)["logits"].double().numpy()
+    want = msa_forward(cfg, sd, tok.numpy(), row_chunk=row_chunk, col_chunk=col_chunk)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-6
+
+
+def test_esm1_oracle_agrees_with_independent_witness():
+    import numpy as np
+    from oracle.fair_esm import OracleModel
+    from oracle.witness import esm1_forward
+    cfg = tiny_config("esm1", 2, 48, 3, 96)
+    sd = synthetic_state_dict(cfg, 17)
+    tok = torch.randint(4, 24, (2, 13), generator=torch.Generator().manual_seed(3))
+    tok[:, 0] = 32
+    tok[1, 4:7] = 33
+    got = OracleModel(cfg, sd).model(tok)["logits"].double().numpy()
+    want = esm1_forward(cfg, sd, tok.numpy())
+    assert np.abs(got - want).max() / np.abs(want).max() < 2e-6
