@@ -740,7 +740,12 @@ static int forward(pgibbs_engine* e, const Schedule& sched_in, int n_chains, int
     p.x = e->x; p.n_seq = e->n_seq; p.T = e->T; p.d = d; p.rows_per_msa = e->R;
     p.mask_idx = c.mask_idx; p.token_dropout = c.token_dropout; p.eps = e->ln_eps;
     ProfScope ps(e, "embed");
-    CK(launch_pdl(embed_kernel, dim3((M + 7) / 8), dim3(256), 0, st, p));
+    const dim3 grid((M + 7) / 8);
+    const int vpl = (d / 4 + 31) / 32;  // float4 vectors per lane
+    if (vpl <= 3) CK(launch_pdl(embed_kernel<3>, grid, dim3(256), 0, st, p));
+    else if (vpl <= 6) CK(launch_pdl(embed_kernel<6>, grid, dim3(256), 0, st, p));
+    else if (vpl <= 10) CK(launch_pdl(embed_kernel<10>, grid, dim3(256), 0, st, p));
+    else CK(launch_pdl(embed_kernel<kMaxVecPerLane>, grid, dim3(256), 0, st, p));
   }
   const int n_layers = e->layer_limit >= 0 ? std::min(e->layer_limit, c.layers) : c.layers;
   for (int li = 0; li < n_layers; ++li) {

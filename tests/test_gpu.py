@@ -683,3 +683,30 @@ def test_full_size_properties_config4_and_5_shards(name, B, L, P, top_k):
     plan, _ = s.plan_positions(B, idx, last_i, P, False, 2)
     out = _full_size_properties(s, toks[:, None], plan, 1, 23, B // 4, top_k=top_k, temperature=None, burnin=1)
     assert out.shape == (B, 1, L + 2)
+
+
+def test_two_engines_on_two_devices_in_one_process():
+    """`pgibbs.h`: one engine per GPU, several per process.  Kernel attributes (the opt-in to > 48 KB of dynamic shared
+    memory) are per device: an engine created on cuda:1 AFTER one on cuda:0 must configure its own device (a
+    process-wide "configured" flag used to skip it -> invalid-argument launch failures).  Both engines give the same
+    logits for the same weights and tokens, and each keeps working after the other has been used."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from protein_gibbs_sampler_b200 import models
+    from protein_gibbs_sampler_b200.config import tiny_config
+    from protein_gibbs_sampler_b200.esm_sampler import ESM_sampler
+    from protein_gibbs_sampler_b200.weights import synthetic_state_dict
+    cfg = tiny_config("roberta_large", 2, 256, 4, 512)      # head_dim 64: tcgen05 GEMM + attention + LM-head kernels
+    sd = synthetic_state_dict(cfg, 4)
+    tok = _tokens(cfg, (2, 258), 5)
+    s0 = ESM_sampler(models.CustomModel(cfg, state_dict=sd), device="cuda:0")
+    a0 = s0.model.model(tok)["logits"]
+    s1 = ESM_sampler(models.CustomModel(cfg, state_dict=sd), device="cuda:1")
+    a1 = s1.model.model(tok)["logits"]
+    assert torch.equal(a0, a1)
+    assert torch.equal(s0.model.model(tok)["logits"], a0)
+    random.seed(1); torch.manual_seed(1)
+    out1 = s1.generate(2, "MKTAYIAKQRQISFVKSHFSRQ", batch_size=2, num_iters=2, top_k=3, show_progress_bar=False)
+    random.seed(1); torch.manual_seed(1)
+    out0 = s0.generate(2, "MKTAYIAKQRQISFVKSHFSRQ", batch_size=2, num_iters=2, top_k=3, show_progress_bar=False)
+    assert out0 == out1
