@@ -43,7 +43,8 @@ struct AttnFaParams {
   int n_seq;
   int n_tiles;  // 128-row query tiles handled here: ceil(T/128), or floor(T/128) when a tail kernel takes the rest
   // Optional timeline (debug): CTA 0 appends (clock64 << 8 | event code) words, kFaTraceCap per traced warp
-  // (0: issuer A, 1: softmax warp 4, 2: issuer B, 3: softmax warp 8).  nullptr = off.
+  // (0: issuer A, 1: softmax warp 4, 2: issuer B, 3: softmax warp 8).  nullptr = off; only -DPGIBBS_FA_TRACE=1 builds
+  // write it.
   unsigned long long* trace;
   int stagger_cycles;  // initial lag of tile B's softmax group behind tile A's (see the softmax role)
   // Trailing query rows [n_tiles*128, T) (at most 8) handled by warp 2 with mma.sync from the K/V blocks that
@@ -69,30 +70,21 @@ __device__ __forceinline__ float fa_ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void fa_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
-                   reinterpret_cast<uint64_t>(m)),
-               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
-               : "memory");
-}
-
-__device__ __forceinline__ void fa_rescale_o(uint32_t taddr, float alpha) {
-#pragma unroll
-  for (int hlf = 0; hlf < 2; ++hlf) {
-    uint32_t o[32];
-    tmem_ld32(taddr + hlf * 32, o);
+#ifndef PGIBBS_FA_TRACE
+#define PGIBBS_FA_TRACE 0
+#endif
+// Rare path (the reference maximum of a row grew by more than the threshold): O *= alpha.  Out of line and 16 columns at
+// a time, so that it does not raise the register pressure of the softmax loop it is called from.
+__device__ __noinline__ void fa_rescale_o(uint32_t taddr, float alpha) {
+#pragma unroll 1
+  for (int c0 = 0; c0 < kFaOCols; c0 += 16) {
+    uint32_t o[16];
+    tmem_ld16(taddr + c0, o);
     tmem_wait_ld();
 #pragma unroll
-    for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-    tmem_st32(taddr + hlf * 32, o);
+    for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+    tmem_st16(taddr + c0, o);
   }
-  uint32_t o[16];
-  tmem_ld16(taddr + 64, o);  // the row sums
-  tmem_wait_ld();
-#pragma unroll
-  for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-  tmem_st16(taddr + 64, o);
 }
 
 __global__ void __launch_bounds__(kFaThreads, 1)
@@ -157,12 +149,19 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
   pdl_wait();               // set-up above overlaps the previous kernel's tail (programmatic dependent launch)
   pdl_launch_dependents();
 
+  // The timeline costs registers and ~6 instructions per point in the softmax loop even when it is switched off (at the
+  // 168-register cap that pushed loop-carried state into local memory, re-loaded in the middle of every hand-over:
+  // 12 % of the kernel), so it only exists in -DPGIBBS_FA_TRACE=1 builds (PGIBBS_NVCC_EXTRA; tools/attn_trace.py).
+#if PGIBBS_FA_TRACE
   const int trace_slot = warp == 1 ? 0 : warp == 4 ? 1 : warp == 3 ? 2 : warp == 8 ? 3 : -1;
   const bool tracing = p.trace != nullptr && blockIdx.x == 0 && lane == 0 && trace_slot >= 0;
   int trace_n = 0;
   auto trace = [&](int code) {
     if (tracing && trace_n < kFaTraceCap) p.trace[trace_slot * kFaTraceCap + trace_n++] = (static_cast<unsigned long long>(clock64()) << 8) | code;
   };
+#else
+  auto trace = [](int) {};
+#endif
 
   // item -> (pair, seq, head): pair-major so that every CTA gets the same mix of full and partial pairs
   auto decode = [&](int item, int& pair, int& seq, int& head) {

@@ -121,6 +121,30 @@ def test_attention_operator(n_seq, T, H, Dh):
     assert rel(op_attention(qkv, n_seq, T, H, Dh), want) < 3e-3   # P and ctx are rounded to fp16
 
 
+@pytest.mark.parametrize("T,hot_keys", [(258, (40,)), (258, (100, 250)), (300, (5, 70, 130, 257, 299)), (1024, (33, 200, 1000)),
+                                        (514, (513,)), (200, (96, 97, 191))])
+def test_attention_operator_growing_maximum(T, hot_keys):
+    """Keys whose scores exceed everything before them by far more than the lazy-rescale threshold (2^11), placed in the
+    first and in the second half of 64-key sub-blocks, early and late in the sequence: exercises the O rescale, the
+    rescale of the half sub-block of P that is already in TMEM, and the trailing-row path of the tcgen05 attention."""
+    from protein_gibbs_sampler_b200.engine import op_attention
+    n_seq, H, Dh = 2, 3, 64
+    g = torch.Generator().manual_seed(T + len(hot_keys))
+    x = torch.randn(n_seq, T, 3, H, Dh, generator=g) * 0.3
+    x[:, :, 2] *= 3
+    u = torch.nn.functional.normalize(torch.randn(H, Dh, generator=g), dim=-1)
+    x[:, :, 0] += 3.0 * u                      # every query has a component along u ...
+    for j, key in enumerate(hot_keys):         # ... and the hot keys are increasingly aligned with it
+        x[:, key, 1] += (8.0 + 6.0 * j) * u
+    qkv = x.reshape(n_seq * T, 3 * H * Dh)
+    xh = qkv.half().float().view(n_seq, T, 3, H, Dh)
+    q, k, v = (xh[:, :, i].transpose(1, 2) for i in range(3))
+    s = q @ k.transpose(-1, -2)
+    assert float((s.max(-1).values - s[..., :hot_keys[0]].max(-1).values).min()) > 9.0   # > 2^11 in every row
+    want = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(n_seq * T, H * Dh)
+    assert rel(op_attention(qkv, n_seq, T, H, Dh), want) < 3e-3
+
+
 def test_sampler_tail_bit_exact_vs_oracle():
     from oracle.sampler_tail import generate_step_with_noise
     from protein_gibbs_sampler_b200.engine import op_sample

@@ -1,5 +1,6 @@
 """Timeline of the tcgen05 attention kernel's CTA 0 (GPU box): per-event clock deltas for the issuer and three
-softmax warps.  python tools/attn_trace.py [T]"""
+softmax warps.  Needs a library built with PGIBBS_NVCC_EXTRA=-DPGIBBS_FA_TRACE=1 (the
+timeline is compiled out of the product kernel).  python tools/attn_trace.py [T]"""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
