@@ -469,6 +469,14 @@ def run_ours(args):
             algorithmic_flops_per_iter(cfg4, 64, 514), peaks, world, ck, _time_single.kernels)
         m4s.model.engine.close()
         del m4s
+        # ... and with only the weights carried as hi + lo pairs (two passes per GEMM: inside 1e-3 on the batch metric)
+        m4w = _model_on_ranks(models, models.ESM2_t33_650M, cfg4, world, rank, dev, precision="split_weights")
+        (_, _, _, ms4w, _), ck = clocked(lambda: _time_single(timer, ESM_sampler, m4w, local, rank, 64, 512, 5, 50, 0, OW, 3))
+        other["C4_shard_split_weights"] = _other_config_entry(
+            "C4", "as C4_shard with precision='split_weights' (fp16 hi+lo weights, two tensor-core passes per GEMM)", ms4w, 3,
+            algorithmic_flops_per_iter(cfg4, 64, 514), peaks, world, ck, _time_single.kernels)
+        m4w.model.engine.close()
+        del m4w
         # config 3: MSA-1b, 16 MSAs x 32 rows x L=128, 10 % of the positions of every row per iteration
         cfg3 = get_config("esm_msa1b_t12_100M_UR50S")
         m3 = _model_on_ranks(models, models.ESM_MSA1, cfg3, world, rank, dev)
