@@ -181,14 +181,14 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         decode(item, pair, seq, head);
         const bool has_b = 2 * pair + 1 < p.n_tiles;
         const int qs = it & 1;
-        mbar_wait(&q_empty[qs], ((it >> 1) & 1) ^ 1);
+        mbar_wait_lean(&q_empty[qs], ((it >> 1) & 1) ^ 1);
         uint8_t* q = sQ + qs * 2 * kFaTile;
         mbar_arrive_expect_tx(&q_full[qs], has_b ? 2 * kFaTile : kFaTile);
         tma_load_3d(q, &tmQKV, &q_full[qs], head * 64, 2 * pair * 128, seq);
         if (has_b) tma_load_3d(q + kFaTile, &tmQKV, &q_full[qs], head * 64, (2 * pair + 1) * 128, seq);
         for (int j = 0; j < nkb; ++j, ++kv_cnt) {
           const int st = kv_cnt % kFaKvStages;
-          mbar_wait(&kv_empty[st], ((kv_cnt / kFaKvStages) & 1) ^ 1);
+          mbar_wait_lean(&kv_empty[st], ((kv_cnt / kFaKvStages) & 1) ^ 1);
           uint8_t* sk = sKV + st * 2 * kFaTile;
           mbar_arrive_expect_tx(&kv_full[st], 2 * kFaTile);
           tma_load_3d(sk, &tmQKV, &kv_full[st], d + head * 64, j * 128, seq);
@@ -228,7 +228,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         // kv_full, so that the arrival lands in the right phase of the ring).
         for (int j = 0; j < nkb; ++j) {
           const uint32_t c = kv_cnt + j;
-          mbar_wait(&kv_full[c % kFaKvStages], (c / kFaKvStages) & 1);
+          mbar_wait_lean(&kv_full[c % kFaKvStages], (c / kFaKvStages) & 1);
           if (issuer) mbar_arrive(&kv_empty[c % kFaKvStages]);
           __syncwarp();
         }
@@ -236,7 +236,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       }
       const int qs = it & 1;
       trace(0x01);  // item begins (issuer)
-      mbar_wait(&q_full[qs], (it >> 1) & 1);
+      mbar_wait_lean(&q_full[qs], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t q_lo = q_lo0 + qs * (2 * kFaTile >> 4);
       // S(i) = Q K_i^T into buffer i & 1.  K rows of sub-block i: stage of block i/2, +8 KB for the odd half.
@@ -252,7 +252,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         }
         __syncwarp();
       };
-      mbar_wait(&kv_full[kv_cnt % kFaKvStages], (kv_cnt / kFaKvStages) & 1);
+      mbar_wait_lean(&kv_full[kv_cnt % kFaKvStages], (kv_cnt / kFaKvStages) & 1);
       tc_fence_after();
       issue_s(0);
       if (nsub > 1) issue_s(1);
@@ -266,10 +266,10 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         // moving the start address by `delta` moves the LBO by -delta.
         const uint32_t delta = st * (2 * kFaTile >> 4) + b * (kFaTile >> 5);
         const uint32_t vd = v_lo0 + delta - (delta << 16);
-        mbar_wait(&p_ready[2 * t + b], (p_par >> b) & 1);
+        mbar_wait_lean(&p_ready[2 * t + b], (p_par >> b) & 1);
         p_par ^= 1u << b;
         trace(0x10 + t);  // P(i) seen
-        if (i == 0) mbar_wait(&o_free[t], (o_par & 1) ^ 1);  // previous item's O has been read out
+        if (i == 0) mbar_wait_lean(&o_free[t], (o_par & 1) ^ 1);  // previous item's O has been read out
         tc_fence_after();
         trace(0x30);  // fences done
         if (issuer) {
@@ -284,7 +284,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         if (i + 2 < nsub) {
           if (b == 0) {  // sub-block i+2 opens the next 128-key block
             const uint32_t c = kv_cnt + (i >> 1) + 1;
-            mbar_wait(&kv_full[c % kFaKvStages], (c / kFaKvStages) & 1);
+            mbar_wait_lean(&kv_full[c % kFaKvStages], (c / kFaKvStages) & 1);
             tc_fence_after();
           }
           issue_s(i + 2);
@@ -315,7 +315,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         if (pair != 0) {  // the tail of this (sequence, head) belongs to its first item; still release the blocks
           for (int j = 0; j < nkb; ++j) {
             const uint32_t c = kv_cnt + j;
-            mbar_wait(&kv_full[c % kFaKvStages], (c / kFaKvStages) & 1);
+            mbar_wait_lean(&kv_full[c % kFaKvStages], (c / kFaKvStages) & 1);
             if (lane == 0) mbar_arrive(&kv_empty[c % kFaKvStages]);
             __syncwarp();
           }
@@ -338,7 +338,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         for (int j = 0; j < nkb; ++j) {
           const uint32_t c = kv_cnt + j;
           const int st = c % kFaKvStages;
-          mbar_wait(&kv_full[st], (c / kFaKvStages) & 1);
+          mbar_wait_lean(&kv_full[st], (c / kFaKvStages) & 1);
           const uint32_t sk = smem_u32(sKV + st * 2 * kFaTile), sv = sk + kFaTile;
           const int nsb = min(2, (T - j * 128 + 63) >> 6);
           for (int sb = 0; sb < nsb; ++sb) {
@@ -477,7 +477,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         if (leader) {
           release_stage();
           // paced by the producer (q_full of THIS item), or two early arrivals could complete one phase
-          mbar_wait(&q_full[qs], (it >> 1) & 1);
+          mbar_wait_lean(&q_full[qs], (it >> 1) & 1);
           mbar_arrive(&q_empty[qs]);
         }
         continue;
@@ -487,7 +487,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       for (int i = 0; i < nsub; ++i) {
         const int b = i & 1;
         trace(0x20);  // waiting for S(i)
-        mbar_wait(&s_full[2 * t + b], (s_par >> b) & 1);
+        mbar_wait_lean(&s_full[2 * t + b], (s_par >> b) & 1);
         s_par ^= 1u << b;
         tc_fence_after();
         trace(0x21);  // S(i) ready
@@ -519,7 +519,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
               const float m_new = fmaxf(m_used, mx);
               if (i > 0) {
                 // O is quiescent once PV(t, i-1) -- completion number pv_cnt + i of pv_done[t] -- has retired
-                mbar_wait(&pv_done[t], (pv_cnt + i - 1) & 1);
+                mbar_wait_lean(&pv_done[t], (pv_cnt + i - 1) & 1);
                 tc_fence_after();
                 fa_rescale_o(tO, fa_ex2(m_used - m_new));
                 tmem_wait_st();
@@ -545,7 +545,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       }
       pv_cnt += nsub;
       // ---- output: O / l -> fp16 -> staging (this tile's Q buffer: every S MMA of the item has retired) -> TMA store
-      mbar_wait(&o_full[t], o_cnt & 1);
+      mbar_wait_lean(&o_full[t], o_cnt & 1);
       ++o_cnt;
       tc_fence_after();
       trace(0x23);  // O complete
