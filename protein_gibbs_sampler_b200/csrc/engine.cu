@@ -831,10 +831,26 @@ static int forward(pgibbs_engine* e, const Schedule& sched_in, int n_chains, int
     if (e->sc_active) { p.targets = e->sc_targets; p.logp_out = e->sc_logp; }
     const size_t emb_bytes = static_cast<size_t>(c.vocab) * d * sizeof(float);
     p.emb_in_smem = emb_bytes <= 200 * 1024;
-    CK(ensure_dynamic_smem(head_sample_kernel, 200 * 1024));
-    const int grid = std::min(num_sms(), (rows + 11) / 12);
+    // Rows per warp: as many (4, 2, 1) as still give every warp of the grid work -- the projection table is streamed
+    // from shared memory once per row group; registers per row sized to the model as for the LayerNorm kernel.
+    const int vpl = (d / 4 + 31) / 32;
+    const size_t smem = p.emb_in_smem ? emb_bytes : 0;
     ProfScope ps(e, "head_sample");
-    CK(launch_pdl(head_sample_kernel, dim3(grid), dim3(384), p.emb_in_smem ? emb_bytes : 0, st, p));
+    auto go = [&](auto kernel, int R, int threads) -> int {
+      const int wpb = threads / 32, units = (rows + R - 1) / R;
+      CK(ensure_dynamic_smem(kernel, 200 * 1024));
+      CK(launch_pdl(kernel, dim3(std::min(num_sms(), (units + wpb - 1) / wpb)), dim3(threads), smem, st, p));
+      return 0;
+    };
+    static int max_r = -1;   // PGIBBS_HEAD_ROWS caps the rows per warp (A/B)
+    if (max_r < 0) { const char* v = getenv("PGIBBS_HEAD_ROWS"); max_r = v ? atoi(v) : 4; }
+    // measured (profiles/r02zq_head_sample_rows_per_warp.txt): 4 rows pay off for d <= 768 once every warp gets several
+    // groups; at d = 1280 four rows need 255 registers (256 threads) and are no faster than two
+    const auto enough = [&](int R, int waves) { return R <= max_r && rows >= R * 12 * num_sms() * waves; };
+    if (vpl <= 6 && enough(4, 2)) TRY(go(head_sample_kernel<4, 6>, 4, 384));
+    else if (vpl <= 10 && enough(2, 1)) TRY(go(head_sample_kernel<2, 10>, 2, 384));
+    else if (vpl <= 10) TRY(go(head_sample_kernel<1, 10>, 1, 384));
+    else TRY(go(head_sample_kernel<1, kMaxVecPerLane>, 1, 384));
   }
   return 0;
 }

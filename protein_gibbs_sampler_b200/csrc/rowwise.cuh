@@ -418,6 +418,10 @@ struct HeadParams {
   float* logp_out;           // [rows] log_softmax(logits)[target] over the whole vocabulary
 };
 
+// R rows per warp, VPL float4 per lane and row (sized to the model like layernorm_kernel).  One pass over the projection
+// table serves the R rows of a warp: the table is read from shared memory once per ROW GROUP, not once per row (at
+// R = 1 every sampled row streams V x d x 4 = 169 KB through the shared-memory port -- the kernel's bound).
+template <int R, int VPL>
 __global__ void __launch_bounds__(384) head_sample_kernel(HeadParams p) {
   extern __shared__ float s_emb[];
   const int lane = threadIdx.x & 31;
@@ -433,113 +437,138 @@ __global__ void __launch_bounds__(384) head_sample_kernel(HeadParams p) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const float* E = p.emb_in_smem ? s_emb : p.emb;
   const int nvec = p.d >> 2;
-  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < p.rows;
-       row += gridDim.x * warps_per_block) {
-    const float4* in = reinterpret_cast<const float4*>(p.g + static_cast<long long>(row) * p.d);
-    float4 v[kMaxVecPerLane];
-    float sum = 0.f;
+  for (int row0 = (blockIdx.x * warps_per_block + (threadIdx.x >> 5)) * R; row0 < p.rows;
+       row0 += gridDim.x * warps_per_block * R) {
+    float4 v[R][VPL];
 #pragma unroll
-    for (int k = 0; k < kMaxVecPerLane; ++k) {
-      const int i = lane + k * 32;
-      if (i < nvec) {
-        v[k] = in[i];
-        sum += v[k].x + v[k].y + v[k].z + v[k].w;
+    for (int r = 0; r < R; ++r) {
+      const bool have = row0 + r < p.rows;
+      const float4* in = reinterpret_cast<const float4*>(p.g + static_cast<long long>(have ? row0 + r : row0) * p.d);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < VPL; ++k) {
+        const int i = lane + k * 32;
+        v[r][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < nvec) {
+          v[r][k] = in[i];
+          sum += v[r][k].x + v[r][k].y + v[r][k].z + v[r][k].w;
+        }
       }
-    }
-    const float mean = warp_sum(sum) / p.d;
-    float sq = 0.f;
+      const float mean = warp_sum(sum) / p.d;
+      float sq = 0.f;
 #pragma unroll
-    for (int k = 0; k < kMaxVecPerLane; ++k) {
-      const int i = lane + k * 32;
-      if (i < nvec) {
-        const float4 a = v[k];
-        sq += (a.x - mean) * (a.x - mean) + (a.y - mean) * (a.y - mean) + (a.z - mean) * (a.z - mean) +
-              (a.w - mean) * (a.w - mean);
+      for (int k = 0; k < VPL; ++k) {
+        const int i = lane + k * 32;
+        if (i < nvec) {
+          const float4 a = v[r][k];
+          sq += (a.x - mean) * (a.x - mean) + (a.y - mean) * (a.y - mean) + (a.z - mean) * (a.z - mean) +
+                (a.w - mean) * (a.w - mean);
+        }
       }
-    }
-    const float rstd = 1.0f / sqrtf(warp_sum(sq) / p.d + p.eps);
+      const float rstd = 1.0f / sqrtf(warp_sum(sq) / p.d + p.eps);
 #pragma unroll
-    for (int k = 0; k < kMaxVecPerLane; ++k) {
-      const int i = lane + k * 32;
-      if (i < nvec && !p.no_ln) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_w) + i);
-        const float4 h = __ldg(reinterpret_cast<const float4*>(p.ln_b) + i);
-        float4 a = v[k];
-        a.x = (a.x - mean) * rstd * g.x + h.x; a.y = (a.y - mean) * rstd * g.y + h.y;
-        a.z = (a.z - mean) * rstd * g.z + h.z; a.w = (a.w - mean) * rstd * g.w + h.w;
-        v[k] = a;
+      for (int k = 0; k < VPL; ++k) {
+        const int i = lane + k * 32;
+        if (i < nvec && !p.no_ln) {
+          const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_w) + i);
+          const float4 h = __ldg(reinterpret_cast<const float4*>(p.ln_b) + i);
+          float4 a = v[r][k];
+          a.x = (a.x - mean) * rstd * g.x + h.x; a.y = (a.y - mean) * rstd * g.y + h.y;
+          a.z = (a.z - mean) * rstd * g.z + h.z; a.w = (a.w - mean) * rstd * g.w + h.w;
+          v[r][k] = a;
+        }
       }
     }
     // vocabulary projection: lane v ends up holding logit v (v < 32); logit 32.. kept in `extra` on lane v-32.
-    // Four tokens at a time: their dot products and the four butterfly reductions are independent chains, which is
-    // what hides the shared-memory and shuffle latency with only 12 warps per SM (per-token arithmetic unchanged).
-    float mine = 0.f, extra = 0.f;
+    // Four tokens at a time: their dot products and the butterfly reductions are independent chains, which is
+    // what hides the shared-memory and shuffle latency with only 12 warps per SM (per-token arithmetic unchanged:
+    // the same products are accumulated in the same order whatever R is).
+    float mine[R], extra[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) mine[r] = extra[r] = 0.f;
     for (int tok0 = 0; tok0 < p.V; tok0 += 4) {
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float acc[R][4];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int tok = tok0 + u < p.V ? tok0 + u : p.V - 1;   // clamp: the surplus lanes of the last group are ignored
         const float4* e = reinterpret_cast<const float4*>(E + static_cast<long long>(tok) * p.d);
 #pragma unroll
-        for (int k = 0; k < kMaxVecPerLane; ++k) {
+        for (int k = 0; k < VPL; ++k) {
           const int i = lane + k * 32;
           if (i < nvec) {
             const float4 w = e[i];
-            acc[u] = fmaf(v[k].x, w.x, acc[u]); acc[u] = fmaf(v[k].y, w.y, acc[u]);
-            acc[u] = fmaf(v[k].z, w.z, acc[u]); acc[u] = fmaf(v[k].w, w.w, acc[u]);
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              acc[r][u] = fmaf(v[r][k].x, w.x, acc[r][u]); acc[r][u] = fmaf(v[r][k].y, w.y, acc[r][u]);
+              acc[r][u] = fmaf(v[r][k].z, w.z, acc[r][u]); acc[r][u] = fmaf(v[r][k].w, w.w, acc[r][u]);
+            }
           }
         }
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[r][u] += __shfl_xor_sync(0xffffffffu, acc[r][u], o);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int tok = tok0 + u;
         if (tok < p.V) {
-          const float a = acc[u] + __ldg(p.out_bias + tok);
-          if ((tok & 31) == lane) { if (tok < 32) mine = a; else extra = a; }
+          const float bias = __ldg(p.out_bias + tok);
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float a = acc[r][u] + bias;
+            if ((tok & 31) == lane) { if (tok < 32) mine[r] = a; else extra[r] = a; }
+          }
         }
       }
     }
-    if (p.logits_out) {
-      float* lo = p.logits_out + static_cast<long long>(row) * p.V;
-      if (lane < p.V) lo[lane] = mine;
-      if (lane + 32 < p.V) lo[lane + 32] = extra;
-    }
-    if (p.logp_out) {
-      const float a = lane < p.V ? mine : -INFINITY, b = lane + 32 < p.V ? extra : -INFINITY;
-      float mx = fmaxf(a, b);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float lse = logf(warp_sum(expf(a - mx) + expf(b - mx))) + mx;
-      const int tgt = __ldg(p.targets + row);
-      const float lt = __shfl_sync(0xffffffffu, tgt >= 32 ? extra : mine, tgt & 31);
-      if (lane == 0) p.logp_out[row] = tgt >= 0 && tgt < p.V ? lt - lse : 0.f;
-    }
-    if (!p.tokens) continue;
-
-    // device-resident iteration (graph replay): the effective k and the noise slice follow from it
-    int iter = p.iter, top_k = p.top_k;
-    const float* noise = p.noise;
-    if (p.sched.iter_dev) {
-      iter = *p.sched.iter_dev;
-      top_k = (iter < p.burnin || p.top_k_raw <= 0 || p.top_k_raw > p.n_valid) ? p.n_valid : p.top_k_raw;
-      if (noise) noise += static_cast<long long>(iter) * p.rows * p.noise_stride;
-    }
-    const int best_id = generate_step_warp(mine, extra, lane, row, iter, p.valid_ids, p.n_valid, top_k,
-                                           p.temperature, noise, p.noise_stride, p.seed, p.rng_row_offset);
-    if (lane == 0) {
-      const int chain = row / p.sched.P, slot = row % p.sched.P;
-      const int32_t* plist = p.sched.positions + iter * p.sched.iter_stride + chain * p.sched.chain_stride;
-      const int pos = plist[slot];
-      bool write = true;
-      if (p.skip_dup_writes) {
-        for (int s2 = slot + 1; s2 < p.sched.P; ++s2) if (plist[s2] == pos) { write = false; break; }
+    for (int r = 0; r < R; ++r) {
+      const int row = row0 + r;
+      if (row >= p.rows) break;
+      const float mine_r = mine[r], extra_r = extra[r];
+      if (p.logits_out) {
+        float* lo = p.logits_out + static_cast<long long>(row) * p.V;
+        if (lane < p.V) lo[lane] = mine_r;
+        if (lane + 32 < p.V) lo[lane + 32] = extra_r;
       }
-      if (write) p.tokens[(static_cast<long long>(chain) * p.sched.seq_stride + p.sched.seq_offset) * p.T + pos] = best_id;
+      if (p.logp_out) {
+        const float a = lane < p.V ? mine_r : -INFINITY, b = lane + 32 < p.V ? extra_r : -INFINITY;
+        float mx = fmaxf(a, b);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        const float lse = logf(warp_sum(expf(a - mx) + expf(b - mx))) + mx;
+        const int tgt = __ldg(p.targets + row);
+        const float lt = __shfl_sync(0xffffffffu, tgt >= 32 ? extra_r : mine_r, tgt & 31);
+        if (lane == 0) p.logp_out[row] = tgt >= 0 && tgt < p.V ? lt - lse : 0.f;
+      }
+      if (!p.tokens) continue;
+
+      // device-resident iteration (graph replay): the effective k and the noise slice follow from it
+      int iter = p.iter, top_k = p.top_k;
+      const float* noise = p.noise;
+      if (p.sched.iter_dev) {
+        iter = *p.sched.iter_dev;
+        top_k = (iter < p.burnin || p.top_k_raw <= 0 || p.top_k_raw > p.n_valid) ? p.n_valid : p.top_k_raw;
+        if (noise) noise += static_cast<long long>(iter) * p.rows * p.noise_stride;
+      }
+      const int best_id = generate_step_warp(mine_r, extra_r, lane, row, iter, p.valid_ids, p.n_valid, top_k,
+                                             p.temperature, noise, p.noise_stride, p.seed, p.rng_row_offset);
+      if (lane == 0) {
+        const int chain = row / p.sched.P, slot = row % p.sched.P;
+        const int32_t* plist = p.sched.positions + iter * p.sched.iter_stride + chain * p.sched.chain_stride;
+        const int pos = plist[slot];
+        bool write = true;
+        if (p.skip_dup_writes) {
+          for (int s2 = slot + 1; s2 < p.sched.P; ++s2) if (plist[s2] == pos) { write = false; break; }
+        }
+        if (write) p.tokens[(static_cast<long long>(chain) * p.sched.seq_stride + p.sched.seq_offset) * p.T + pos] = best_id;
+      }
     }
   }
 }
