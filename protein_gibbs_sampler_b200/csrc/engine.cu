@@ -842,8 +842,8 @@ static int forward(pgibbs_engine* e, const Schedule& sched_in, int n_chains, int
       CK(launch_pdl(kernel, dim3(std::min(num_sms(), (units + wpb - 1) / wpb)), dim3(threads), smem, st, p));
       return 0;
     };
-    static int max_r = -1;   // PGIBBS_HEAD_ROWS caps the rows per warp (A/B)
-    if (max_r < 0) { const char* v = getenv("PGIBBS_HEAD_ROWS"); max_r = v ? atoi(v) : 4; }
+    const char* cap = getenv("PGIBBS_HEAD_ROWS");   // caps the rows per warp (A/B, and the R-invariance test)
+    const int max_r = cap ? atoi(cap) : 4;
     // measured (profiles/r02zq_head_sample_rows_per_warp.txt): 4 rows pay off for d <= 768 once every warp gets several
     // groups; at d = 1280 four rows need 255 registers (256 threads) and are no faster than two
     const auto enough = [&](int R, int waves) { return R <= max_r && rows >= R * 12 * num_sms() * waves; };

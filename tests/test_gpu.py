@@ -274,6 +274,27 @@ def test_forward_logits_precise_mode(arch, layers, d, H, F, shape):
     assert e["batch"] < LOGIT_TOL and e["row"] < LOGIT_TOL and e["rms"] < 0.25 * LOGIT_TOL
 
 
+@pytest.mark.parametrize("arch,d,H,shape", [("esm2", 128, 2, (72, 258)),        # 18 576 rows, d = 128: four rows per warp
+                                            ("esm2", 640, 10, (20, 258)),       # 5 160 rows, d = 640: two rows per warp
+                                            ("msa_transformer", 128, 2, (2, 60, 129))])
+def test_lm_head_rows_per_warp_invariance(arch, d, H, shape, monkeypatch):
+    """The LM-head kernel lets a warp carry 1, 2 or 4 rows through one pass over the projection table, chosen from the
+    number of sampled rows; the per-row arithmetic must not depend on that choice (a chain's logits are the same in
+    every batch), and every variant must agree with the oracle."""
+    from oracle.fair_esm import OracleModel
+    from protein_gibbs_sampler_b200.config import tiny_config
+    cfg = tiny_config(arch, 2, d, H, 2 * d)
+    tok = _tokens(cfg, shape, 9)
+    got = {}
+    for cap in ("1", "2", "4"):
+        monkeypatch.setenv("PGIBBS_HEAD_ROWS", cap)
+        s, sd = make(cfg, 4)
+        got[cap] = s.model.model(tok)["logits"]
+    assert torch.equal(got["1"], got["2"]) and torch.equal(got["1"], got["4"])
+    want = OracleModel(cfg, sd).model(tok)["logits"]
+    assert rel(got["4"], want) < LOGIT_TOL
+
+
 def test_forward_logits_split_weights_mode_config4_shape():
     """The middle level (`precision="split_weights"`: weights as fp16 hi + lo pairs, activations single fp16; two passes
     per GEMM): ESM-2 650M at config 4's token shape is inside north_star's 1e-3 on the batch metric (the per-row metric
