@@ -295,11 +295,12 @@ def test_lm_head_rows_per_warp_invariance(arch, d, H, shape, monkeypatch):
     assert rel(got["4"], want) < LOGIT_TOL
 
 
-def test_forward_logits_split_weights_mode_config4_shape():
+@pytest.mark.parametrize("arch,shape", [("esm2", (2, 514)), ("roberta_large", (2, 258))])   # configs 4 and 2
+def test_forward_logits_split_weights_mode_config_shapes(arch, shape):
     """The middle level (`precision="split_weights"`: weights as fp16 hi + lo pairs, activations single fp16; two passes
-    per GEMM): ESM-2 650M at config 4's token shape is inside north_star's 1e-3 on the batch metric (the per-row metric
-    needs the activations' lo halves as well, i.e. "split")."""
-    e = _forward_errors("esm2", 33, 1280, 20, 5120, (2, 514), precision="split_weights")
+    per GEMM): the 650M models at the token shapes of configs 4 and 2 are inside north_star's 1e-3 on the batch metric
+    (the per-row metric needs the activations' lo halves as well, i.e. "split")."""
+    e = _forward_errors(arch, 33, 1280, 20, 5120, shape, precision="split_weights")
     assert e["batch"] < LOGIT_TOL and e["row"] < ROW_TOL_FAST and e["rms"] < 0.4 * LOGIT_TOL
 
 
