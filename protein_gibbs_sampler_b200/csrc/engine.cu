@@ -271,14 +271,16 @@ __global__ void f16_to_f32_kernel(const __half* __restrict__ in, float* __restri
   const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (i < n) out[i] = __half2float(in[i]);
 }
-__global__ void rope_table_kernel(float2* tab, int T, int half) {
+// row t: [cos(t f_0) .. cos(t f_{half-1}) | sin(t f_0) .. sin(t f_{half-1})]  (the layout rope_chunk loads, gemm.cuh)
+__global__ void rope_table_kernel(float* tab, int T, int half) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T * half) return;
   const int t = i / half, j = i % half;
   // inv_freq = 1 / 10000^(2j/Dh), angle = t * inv_freq  (fair-esm rotary_embedding.py), in fp32 like torch
   const float inv_freq = 1.0f / powf(10000.0f, static_cast<float>(2 * j) / static_cast<float>(2 * half));
   const float ang = static_cast<float>(t) * inv_freq;
-  tab[i] = make_float2(cosf(ang), sinf(ang));
+  tab[static_cast<size_t>(t) * 2 * half + j] = cosf(ang);
+  tab[static_cast<size_t>(t) * 2 * half + half + j] = sinf(ang);
 }
 
 static int to_f16(const float* in, __half* out, long long n, cudaStream_t st) {
@@ -330,7 +332,7 @@ struct pgibbs_engine {
   __half* w_dense = nullptr;
   float* b_dense = nullptr;
   CUtensorMap m_wdense;
-  float2* rope = nullptr;
+  float* rope = nullptr;
   int rope_T = 0;
   // activations
   // T = token rows per sequence on the device = Tu (the caller's tokens per sequence) + 1 for ESM-1, whose extra
@@ -568,7 +570,7 @@ static int allocate_shape(pgibbs_engine* e, int B, int R, int T) {
   TRY(build_weight_maps(e));
   if (e->cfg.arch == PGIBBS_ARCH_ESM2 && e->rope_T < T) {
     if (e->rope) cudaFree(e->rope);
-    TRY(dev_alloc(&e->rope, static_cast<size_t>(T) * (hd / 2)));
+    TRY(dev_alloc(&e->rope, static_cast<size_t>(T) * hd));
     rope_table_kernel<<<(T * (hd / 2) + 255) / 256, 256, 0, e->stream>>>(e->rope, T, hd / 2);
     CK(cudaGetLastError());
     e->rope_T = T;

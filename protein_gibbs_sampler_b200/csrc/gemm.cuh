@@ -41,7 +41,7 @@ struct GemmParams {
   int rope_cols;        // columns [0,rope_cols) get rotary embedding (0 = none); heads are head_dim wide
   int head_dim;
   int seq_len;          // token position t = row % seq_len
-  const float2* rope;   // [seq_len, head_dim/2] (cos, sin)
+  const float* rope;    // [seq_len][cos_0 .. cos_{H-1} | sin_0 .. sin_{H-1}], H = head_dim / 2
   // EPI_RESID_F32 only: K-split of the partly-filled last wave (see gemm_work_unit).  split <= 1: off.
   int reverse;          // walk the tiles from the last row block down (see pgibbs_engine::zigzag)
   int split;            // parts each last-wave tile is cut into along K
@@ -134,18 +134,35 @@ __host__ __device__ constexpr bool epi_out_f16(int epi) { return epi == EPI_BIAS
 constexpr int kEpiStageBytes = 4096;                           // 32 rows x 128 B, one warp's chunk
 constexpr int kEpiStagingTotal = kEpiWarps * 2 * kEpiStageBytes;  // double-buffered per warp
 
-// rotary embedding on one 64-column chunk (chunk start is head-aligned): x*cos + rotate_half(x)*sin
+// rotary embedding on one 64-column chunk (chunk start is head-aligned): x*cos + rotate_half(x)*sin.
+// Table row of token t: [cos_0 .. cos_{H-1} | sin_0 .. sin_{H-1}], H = head_dim / 2, so that four consecutive cosines (sines)
+// come in with one 16-byte load and sit in adjacent registers: the rotation then runs on packed fp32 pairs (FMUL2 / FFMA2,
+// one issue slot per two values -- the epilogue warps share their schedulers with the TMA producer and the MMA issuer, and
+// at ESM-2's shapes this epilogue is what fills them).
+__device__ __forceinline__ uint64_t f32x2_of(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 template <int HD>
-__device__ __forceinline__ void rope_chunk(float (&v)[64], const float2* __restrict__ cs) {
+__device__ __forceinline__ void rope_chunk(float (&v)[64], const float* __restrict__ cs) {
   constexpr int H = HD / 2;
+  static_assert(H % 4 == 0, "head_dim is a multiple of 8");
 #pragma unroll
   for (int h0 = 0; h0 < 64; h0 += HD) {
 #pragma unroll
-    for (int j = 0; j < H; ++j) {
-      const float2 c = __ldg(cs + j);
-      const float a = v[h0 + j], b = v[h0 + j + H];
-      v[h0 + j] = a * c.x - b * c.y;      // first half: -x2*sin
-      v[h0 + j + H] = b * c.x + a * c.y;  // second half: +x1*sin
+    for (int j = 0; j < H; j += 4) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(cs + j));
+      const float4 sn = __ldg(reinterpret_cast<const float4*>(cs + H + j));
+#pragma unroll
+      for (int u = 0; u < 4; u += 2) {
+        const uint64_t a = f32x2_of(v[h0 + j + u], v[h0 + j + u + 1]), b = f32x2_of(v[h0 + j + u + H], v[h0 + j + u + 1 + H]);
+        const uint64_t c2 = u ? f32x2_of(c.z, c.w) : f32x2_of(c.x, c.y), s2 = u ? f32x2_of(sn.z, sn.w) : f32x2_of(sn.x, sn.y);
+        uint64_t ac, bc, bs, na, nb;
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(ac) : "l"(a), "l"(c2));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(bc) : "l"(b), "l"(c2));
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(bs) : "l"(b), "l"(s2));
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(na) : "l"(ac), "l"(bs));                    // first half: -x2*sin (FADD2, negated operand)
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(nb) : "l"(a), "l"(s2), "l"(bc));        // second half: +x1*sin
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(v[h0 + j + u]), "=f"(v[h0 + j + u + 1]) : "l"(na));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(v[h0 + j + u + H]), "=f"(v[h0 + j + u + 1 + H]) : "l"(nb));
+      }
     }
   }
 }
@@ -253,7 +270,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
       }
       if (g < p.rope_cols) {
         const int t = (row0 + lane) % p.seq_len;
-        const float2* cs = p.rope + static_cast<size_t>(t) * (p.head_dim >> 1);
+        const float* cs = p.rope + static_cast<size_t>(t) * p.head_dim;
         if (p.head_dim == 64) rope_chunk<64>(v, cs);
         else if (p.head_dim == 32) rope_chunk<32>(v, cs);
         else rope_chunk<16>(v, cs);
