@@ -484,6 +484,16 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
       }
       const bool warp_live = tile * 128 + quad * 32 < T;  // warp-uniform: any valid query row in this warp
       float m_used = -INFINITY;                           // reference maximum (log2 domain)
+      if (!warp_live) {  // no valid query row in this warp: only keep the hand-shakes going (off the common path's loop)
+        for (int i = 0; i < nsub; ++i) {
+          const int b = i & 1;
+          mbar_wait_lean(&s_full[2 * t + b], (s_par >> b) & 1);
+          s_par ^= 1u << b;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_ready[2 * t + b]);
+        }
+      } else
       for (int i = 0; i < nsub; ++i) {
         const int b = i & 1;
         trace(0x20);  // waiting for S(i)
@@ -491,12 +501,13 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         s_par ^= 1u << b;
         tc_fence_after();
         trace(0x21);  // S(i) ready
-        if (warp_live) {
+        {
           const int rem = T - i * 64;                     // valid keys in this sub-block (>= 1)
           const uint32_t tSb = tS + b * 64;
           // `W` score columns: reference update (lazy), P = 2^(s - m) as packed fp16 over the consumed scores
-          auto chunk = [&](auto wtag) {
+          auto chunk = [&](auto wtag, auto etag) {
             constexpr int W = decltype(wtag)::value;
+            constexpr bool kEdge = decltype(etag)::value;   // the last sub-block of the sequence: keys beyond T are masked
             float v[W];
             {
               uint32_t r[W];  // both 32-column loads in flight before the single wait
@@ -506,7 +517,7 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
 #pragma unroll
               for (int c = 0; c < W; ++c) v[c] = __uint_as_float(r[c]);
             }
-            if (rem < W) {                                // sequence edge: keys >= T do not exist
+            if (kEdge && rem < W) {                       // sequence edge: keys >= T do not exist
 #pragma unroll
               for (int c = 0; c < W; ++c)
                 if (c >= rem) v[c] = -INFINITY;
@@ -527,14 +538,29 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
               m_used = m_new;
             }
             uint32_t pk[W / 2];
+            {
+              // x = s log2e - m on packed fp32 pairs (fma.rn.f32x2 -> FFMA2): the FMA pipe spends the same time per result,
+              // but a pair costs one issue slot, and the softmax warps' issue slots are the kernel's time (-2.4 / -3.3 /
+              // -3.5 % at T = 258 / 514 / 1024)
+              uint64_t sc, nm;
+              asm("mov.b64 %0, {%1, %1};" : "=l"(sc) : "f"(kLog2e));
+              asm("mov.b64 %0, {%1, %1};" : "=l"(nm) : "f"(-m_used));
 #pragma unroll
-            for (int c = 0; c < W; c += 2) {
-              __half2 h = __floats2half2_rn(fa_ex2(fmaf(v[c], kLog2e, -m_used)), fa_ex2(fmaf(v[c + 1], kLog2e, -m_used)));
-              pk[c >> 1] = *reinterpret_cast<uint32_t*>(&h);
+              for (int c = 0; c < W; c += 2) {
+                uint64_t x;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "f"(v[c]), "f"(v[c + 1]));
+                asm("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(x) : "l"(sc), "l"(nm));
+                float x0, x1;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(x0), "=f"(x1) : "l"(x));
+                pk[c >> 1] = f2h2_rn(fa_ex2(x0), fa_ex2(x1));
+              }
             }
             if constexpr (W == 64) tmem_st32(tSb, pk); else tmem_st16(tSb, pk);
           };
-          if (rem > 32) chunk(std::integral_constant<int, 64>{}); else chunk(std::integral_constant<int, 32>{});
+          // every sub-block but the last is full: no edge test, no masking code, no width choice on the common path
+          if (i + 1 < nsub) chunk(std::integral_constant<int, 64>{}, std::false_type{});
+          else if (rem > 32) chunk(std::integral_constant<int, 64>{}, std::true_type{});
+          else chunk(std::integral_constant<int, 32>{}, std::true_type{});
           tmem_wait_st();
         }
         tc_fence_before();
@@ -567,7 +593,13 @@ attention_fa_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_cons
         for (int q = 0; q < 8; ++q) {
           float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(o[8 * q + j]) * inv;
+          for (int j = 0; j < 8; j += 2) {   // packed fp32 pairs: one issue slot per two values
+            uint64_t x, iv;
+            asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(o[8 * q + j]), "r"(o[8 * q + j + 1]));
+            asm("mov.b64 %0, {%1, %1};" : "=l"(iv) : "f"(inv));
+            asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(iv));
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(f[j]), "=f"(f[j + 1]) : "l"(x));
+          }
           const uint4 w = make_uint4(f2h2_sat(f[0], f[1]), f2h2_sat(f[2], f[3]), f2h2_sat(f[4], f[5]), f2h2_sat(f[6], f[7]));
           *reinterpret_cast<uint4*>(rowp + ((q ^ (r & 7)) << 4)) = w;  // 128B swizzle, matches tmCtx
           if (lo_row)
