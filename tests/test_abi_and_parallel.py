@@ -33,6 +33,27 @@ def test_library_exports_every_declared_symbol():
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="CPU box behaviour")
+def test_attention_kernel_keeps_its_loop_state_in_registers():
+    """ptxas report of the last build (build.log, -Xptxas -v): the tcgen05 attention kernel must not use local memory.
+    Round 2 measured what it costs when it does -- a never-executed debug timeline and a printf pushed the kernel to the
+    168-register cap, the softmax loop re-loaded its loop-carried state from local memory in every hand-over: 12 % of
+    the kernel (profiles/r02_attention_experiments.txt)."""
+    log = os.path.join(ROOT, "protein_gibbs_sampler_b200", "build.log")
+    if not os.path.exists(log):
+        pytest.skip("no build.log (library built elsewhere)")
+    lines = open(log).read().splitlines()
+    hits = [i for i, l in enumerate(lines) if "Compiling entry function" in l and "attention_fa_kernel" in l]
+    if not hits:
+        pytest.skip("build.log has no ptxas report for the attention kernel")
+    for i in hits:
+        report = " ".join(lines[i:i + 4])
+        m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", report)
+        regs = re.search(r"Used (\d+) registers", report)
+        assert m and regs, report
+        assert (int(m.group(1)), int(m.group(2)), int(m.group(3))) == (0, 0, 0), report
+        assert int(regs.group(1)) <= 160, report   # 384 threads: the cap is 168
+
+
 def test_create_fails_loudly_without_gpu():
     lib = _lib.load()
     cfg = _lib.ModelConfig(arch=1, layers=1, embed_dim=64, heads=2, ffn_dim=128, vocab=33, max_positions=1024,
