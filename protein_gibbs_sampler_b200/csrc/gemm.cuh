@@ -128,6 +128,9 @@ __device__ __forceinline__ void gelu_erf2(float& v0, float& v1) {
   asm("mov.b64 {%0, %1}, %2;" : "=f"(v0), "=f"(v1) : "l"(r));
 }
 
+#ifndef PGIBBS_BIAS_EARLY
+#define PGIBBS_BIAS_EARLY 1
+#endif
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) { return f2h2_sat(a, b); }
 
 __host__ __device__ constexpr bool epi_out_f16(int epi) { return epi == EPI_BIAS_F16 || epi == EPI_GELU_F16 || epi == EPI_QKV_F16; }
@@ -234,6 +237,18 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
     const int g = n0 + c * kCW;
     if (g >= p.N) break;  // warp-uniform: chunk entirely beyond the N edge
     float v[kCW];
+    // fp32 epilogues (32-column chunks; the residual one is the tile period of the short-K out-projection): fetch the
+    // chunk's bias BEFORE the TMEM load so that the two latencies overlap (the volatile tcgen05.ld / wait pair keeps
+    // the compiler from hoisting the loads itself; ncu: the first bias add was the epilogue's second-largest stall).
+    constexpr bool kBiasEarly = !kOut16 && PGIBBS_BIAS_EARLY;
+    float4 bq[kBiasEarly ? kCW / 4 : 1];
+    const bool bias_early = kBiasEarly && p.bias && add_bias && g + kCW <= p.N;
+    if constexpr (kBiasEarly) {
+      if (bias_early) {
+#pragma unroll
+        for (int j4 = 0; j4 < kCW / 4; ++j4) bq[j4] = __ldg(reinterpret_cast<const float4*>(p.bias + g) + j4);
+      }
+    }
 #pragma unroll
     for (int hlf = 0; hlf < kCW / 32; ++hlf) {
       uint32_t r[32];
@@ -242,7 +257,14 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[hlf * 32 + j] = __uint_as_float(r[j]);
     }
-    if (p.bias && add_bias) {
+    if (bias_early) {
+      if constexpr (kBiasEarly) {
+#pragma unroll
+        for (int j4 = 0; j4 < kCW / 4; ++j4) {
+          v[4 * j4 + 0] += bq[j4].x; v[4 * j4 + 1] += bq[j4].y; v[4 * j4 + 2] += bq[j4].z; v[4 * j4 + 3] += bq[j4].w;
+        }
+      }
+    } else if (p.bias && add_bias) {
       if (g + kCW <= p.N) {
 #pragma unroll
         for (int j4 = 0; j4 < kCW / 4; ++j4) {

@@ -319,8 +319,21 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
   return r;
 }
+// Arrive on an mbarrier of another CTA of the cluster.  What the arrival publishes here are completed TMEM reads
+// (tcgen05.wait::ld + tcgen05.fence::before_thread_sync precede it), so the default semantics are enough: one
+// SYNCS.ARRIVE.  `.release.cluster` compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the arrival, which
+// waits for the thread's outstanding TMA reduce-adds to land -- ~6 000 cycles per tile on the epilogue warps of the
+// out-projection (ncu stall samples: 29 % of an epilogue warp's time), the tile period of that short-K GEMM.
+// -DPGIBBS_ARRIVE_RELEASE_CLUSTER=1 restores the old form for A/B runs.
+#ifndef PGIBBS_ARRIVE_RELEASE_CLUSTER
+#define PGIBBS_ARRIVE_RELEASE_CLUSTER 0
+#endif
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+#if PGIBBS_ARRIVE_RELEASE_CLUSTER
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#else
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+#endif
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;  // clears the CTA-rank bit of a pair: address -> leader CTA
 // Load issued by either CTA of the pair; the bytes are accounted on the LEADER's mbarrier.
