@@ -19,3 +19,10 @@ echo "== ncu launch list (timed region of bench.py, 2 steps, config 2 only)"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 600 --csv \
     --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs > $OUT/${TAG}_ncu_bench.log 2>&1
 echo "ncu list exit $?"; wc -l $OUT/${TAG}_launches.csv
+if [ -n "$NCU_GEMM" ]; then
+echo "== ncu --set full on the GEMMs of one layer"
+timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off \
+    -k regex:gemm_tcgen05 -s 8 -c 4 -o $OUT/${TAG}_gemm python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-other-configs \
+    > $OUT/${TAG}_ncu_gemm.log 2>&1
+echo "ncu full exit $?"; ls -la $OUT/${TAG}_gemm.ncu-rep
+fi
