@@ -127,6 +127,8 @@ static int num_sms() {
 // The B tensor map's box holds bn / cg rows.
 constexpr int kSplitFlagInts = 4096;  // K-split flags: >= 148 groups x 2 ranks x 8 epilogue warps
 static int g_gemm_split = 0;              // PGIBBS_GEMM_SPLIT=1: last-wave K-split of the residual GEMMs (off: it makes a chain's low-order bits depend on the batch it runs in)
+static int g_epi_direct = 6;          // PGIBBS_EPI_DIRECT bit mask: plain-store GEMM epilogues write straight from registers (st.global.v8)
+                                      // instead of through shared-memory staging and the TMA engine -- 2: fp16 outputs, 4: fp32 outputs; 0: all TMA
 static int g_pdl = 1;                 // PGIBBS_PDL=0: plain stream-ordered launches
 static int g_graph = 1;               // PGIBBS_GRAPH=0: every iteration is launched kernel by kernel
 static int g_zigzag = 1;              // PGIBBS_ZIGZAG=0: every kernel walks its rows in ascending order
@@ -168,6 +170,12 @@ static int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const Ge
     const int tiles = m_tiles * n_tiles, rem = tiles % groups;
     if (tiles > groups && rem) q.split = std::min({groups / rem, 4, p.K / kBK / 32, kSplitFlagInts / (rem * CG * kEpiWarps)});
     if (q.split < 2) q.split = 1;
+  }
+  {
+    const int bit = epi_out_f16(EPI) ? 2 : 4;
+    const size_t pitch = static_cast<size_t>(p.ldo) * (epi_out_f16(EPI) ? 2 : 4);
+    q.direct = EPI != EPI_RESID_F32 && (g_epi_direct & bit) && !(reinterpret_cast<uintptr_t>(p.out) & 31) &&
+               pitch % 32 == 0 && p.N % 16 == 0 && p.lo_off % 16 == 0;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(groups * CG);
@@ -969,6 +977,7 @@ int pgibbs_create(const pgibbs_model_config* cfg, int32_t device_id, pgibbs_engi
   if (prop.major != 10) return fail("device %d is sm_%d%d; this engine only runs on sm_100 (B200)", device_id, prop.major, prop.minor);
   if (const char* f = getenv("PGIBBS_GEMM_CG")) g_force_cg = atoi(f);
   if (const char* f = getenv("PGIBBS_GEMM_SPLIT")) g_gemm_split = atoi(f);
+  if (const char* f = getenv("PGIBBS_EPI_DIRECT")) g_epi_direct = atoi(f);
   if (const char* f = getenv("PGIBBS_PDL")) g_pdl = atoi(f);
   if (const char* f = getenv("PGIBBS_GRAPH")) g_graph = atoi(f);
   if (const char* f = getenv("PGIBBS_ZIGZAG")) g_zigzag = atoi(f);
@@ -1379,6 +1388,7 @@ int pgibbs_op_gemm(int32_t device_id, const float* A, const float* B, const floa
   cudaStream_t st = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (const char* f = getenv("PGIBBS_GEMM_SPLIT")) g_gemm_split = atoi(f);
+  if (const char* f = getenv("PGIBBS_EPI_DIRECT")) g_epi_direct = atoi(f);
   auto body = [&]() -> int {
     TRY(dev_alloc(&dflags, static_cast<size_t>(kSplitFlagInts)));
     CK(cudaMemset(dflags, 0, kSplitFlagInts * sizeof(int32_t)));

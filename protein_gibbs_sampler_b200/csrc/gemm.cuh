@@ -56,6 +56,14 @@ struct GemmParams {
   int k_segs;
   int lo_off;           // fp16-output epilogues: also store the rounding residual of every output at column + lo_off
                         // (the a_lo half of the next GEMM's A operand); 0 = off
+  // Output path of the plain-store epilogues (everything but EPI_RESID_F32).  0: every 32-row x 128-byte chunk is staged
+  // in shared memory and leaves through the TMA engine -- the engine and the shared-memory port the operand ring
+  // lives on.  1: the chunk goes out straight from registers, one row per lane, as four 32-byte st.global.v8; needs a
+  // 32-byte aligned output with a 32-byte multiple pitch.  (FC1 -2.7 % per launch at config 2.  The residual epilogue
+  // stays on the TMA reduce-add: red.global.add.v4.f32 from registers and a register read-modify-write with
+  // 32-byte loads issued a chunk ahead both measured 17-19 % SLOWER on the out-projection,
+  // profiles/r02zzz10_epilogue_direct_ab.txt.)
+  int direct;
 };
 
 constexpr int kBM = 128;
@@ -317,6 +325,44 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CU
       }
       sbuf ^= 1;
     };
+    if (EPI != EPI_RESID_F32 && p.direct) {
+      // one output row per lane (row0 + lane), kCW consecutive columns from g: 128 bytes = 4 x 32-byte stores; rows
+      // beyond M and column groups beyond N (a multiple of 16) are skipped here -- the TMA path gets that clipping
+      // from the tensor map
+      const int row = row0 + lane;
+      if (row < p.M) {
+        if constexpr (kOut16) {
+          __half* dst = reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.ldo + g;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (g + 16 * q + 16 > p.N) break;
+            const float* x = v + 16 * q;
+            const uint4 a = make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]), pack_half2(x[6], x[7]));
+            const uint4 b = make_uint4(pack_half2(x[8], x[9]), pack_half2(x[10], x[11]), pack_half2(x[12], x[13]), pack_half2(x[14], x[15]));
+            st_global_v8(dst + 16 * q, a, b);
+            if constexpr (EPI == EPI_GELU_F16) {
+              if (p.lo_off)
+                st_global_v8(dst + p.lo_off + 16 * q,
+                             make_uint4(f2h2_residual(x[0], x[1], a.x), f2h2_residual(x[2], x[3], a.y),
+                                        f2h2_residual(x[4], x[5], a.z), f2h2_residual(x[6], x[7], a.w)),
+                             make_uint4(f2h2_residual(x[8], x[9], b.x), f2h2_residual(x[10], x[11], b.y),
+                                        f2h2_residual(x[12], x[13], b.z), f2h2_residual(x[14], x[15], b.w)));
+            }
+          }
+        } else {
+          float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.ldo + g;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (g + 8 * q + 8 > p.N) break;
+            const float* x = v + 8 * q;
+            st_global_v8(dst + 8 * q,
+                         make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3])),
+                         make_uint4(__float_as_uint(x[4]), __float_as_uint(x[5]), __float_as_uint(x[6]), __float_as_uint(x[7])));
+          }
+        }
+      }
+      continue;
+    }
     uint4 w[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {

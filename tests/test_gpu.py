@@ -89,6 +89,23 @@ def test_gemm_operator(M, N, K, bn):
     assert rel(op_gemm(A, B, bias, C=C0, epilogue=2, block_n=bn), want + C0) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(300, 320, 320, 64), (129, 336, 128, 128), (2050, 5120, 1280, 256), (16512, 1280, 1280, 256)])
+def test_gemm_output_paths_bit_identical(M, N, K, bn, monkeypatch):
+    """The plain-store epilogues write either straight from registers (st.global.v8, the default) or through
+    shared-memory staging and the TMA engine (PGIBBS_EPI_DIRECT=0): same values, same clipping at the M / N edges (the
+    TMA path gets it from the tensor map, the direct path from its own guards) -- every output bit must agree."""
+    from protein_gibbs_sampler_b200.engine import op_gemm
+    g = torch.Generator().manual_seed(M ^ N)
+    A, B, bias = torch.randn(M, K, generator=g) * 0.5, torch.randn(N, K, generator=g) * 0.5, torch.randn(N, generator=g)
+    for epi in (0, 1, 4, 5):
+        monkeypatch.setenv("PGIBBS_EPI_DIRECT", "6")
+        direct = op_gemm(A, B, bias, epilogue=epi, block_n=bn)
+        monkeypatch.setenv("PGIBBS_EPI_DIRECT", "0")
+        staged = op_gemm(A, B, bias, epilogue=epi, block_n=bn)
+        assert torch.equal(direct, staged), "epilogue %d" % epi
+    monkeypatch.delenv("PGIBBS_EPI_DIRECT")
+
+
 def test_gemm_operator_config2_rows_vs_torch():
     """The GEMM shapes of BASELINE config 2 (M = 64 x 258 = 16512 token rows: 65 row blocks, partly filled last wave)
     against torch on the same fp16-rounded operands: out-projection (residual epilogue) and FC1 (GELU epilogue)."""
