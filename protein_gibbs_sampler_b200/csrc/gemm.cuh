@@ -229,9 +229,10 @@ __device__ __forceinline__ void st_release_gpu(int32_t* p, int v) {
 }
 
 // Drain one accumulator tile row-slice.  This warp owns TMEM lanes [quad*32, quad*32+32) (= 32 output rows, one per
-// thread) and every second chunk (`par`) of 128 output bytes per row (64 fp16 / 32 fp32 columns).  Each chunk is
-// staged in this warp's own 128B-swizzled shared-memory buffer and written by one TMA store (or TMA reduce-add
-// for the residual stream), so global writes are full lines, asynchronous, and clipped at the M / N edges.
+// thread) and every second chunk (`par`) of 128 output bytes per row (64 fp16 / 32 fp32 columns).  Plain outputs leave
+// straight from the registers as four 32-byte stores per lane (GemmParams::direct); the residual stream -- and plain
+// outputs whose buffer is not 32-byte aligned -- are staged chunk by chunk in this warp's own 128B-swizzled
+// shared-memory buffer and handed to one TMA reduce-add (store): full lines, asynchronous, clipped at the M / N edges.
 //   t_row = TMEM address of the slice's column 0; row0 = first output row of the slice; n0 = first output column.
 template <int BN, int EPI>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, const CUtensorMap* tmC, uint32_t t_row,
