@@ -129,11 +129,13 @@ constexpr int kSplitFlagInts = 4096;  // K-split flags: >= 148 groups x 2 ranks 
 static int g_gemm_split = 0;              // PGIBBS_GEMM_SPLIT=1: last-wave K-split of the residual GEMMs (off: it makes a chain's low-order bits depend on the batch it runs in)
 static int g_epi_direct = 6;          // PGIBBS_EPI_DIRECT bit mask: plain-store GEMM epilogues write straight from registers (st.global.v8)
                                       // instead of through shared-memory staging and the TMA engine -- 2: fp16 outputs, 4: fp32 outputs; 0: all TMA
+static int g_tail_overlap = 1;        // PGIBBS_TAIL_OVERLAP=0: no fork -- by default the LayerNorm of the finished row blocks runs next to a residual GEMM's partly-filled last wave
 static int g_pdl = 1;                 // PGIBBS_PDL=0: plain stream-ordered launches
 static int g_graph = 1;               // PGIBBS_GRAPH=0: every iteration is launched kernel by kernel
 static int g_zigzag = 1;              // PGIBBS_ZIGZAG=0: every kernel walks its rows in ascending order
 constexpr int kGraphMinIters = 16;    // shorter runs do not pay for capture + instantiation (~1 ms)
 
+static thread_local bool t_no_pdl = false;   // set around a launch whose predecessor is an event of another stream
 // Launch with programmatic dependent launch allowed: the kernel must call pdl_wait() before it touches global memory.
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
@@ -142,7 +144,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+  attr[0].val.programmaticStreamSerializationAllowed = (g_pdl && !t_no_pdl) ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }          // PGIBBS_GEMM_SPLIT=0 turns the last-wave K-split off (A/B measurements)
@@ -162,10 +164,12 @@ static int launch_gemm_inst(const CUtensorMap& a, const CUtensorMap& b, const Ge
   if (p.lo_off && (p.N % 64 || p.lo_off < p.N)) return fail("split-operand output needs N %% 64 == 0 and lo_off >= N");
   CK(ensure_dynamic_smem(gemm_tcgen05_kernel<BN, EPI, CG>, gemm_smem_bytes(BN, CG)));
   const int m_tiles = (p.M + kBM * CG - 1) / (kBM * CG), n_tiles = (p.N + BN - 1) / BN;
-  const int groups = std::min(num_sms() / CG, m_tiles * n_tiles);
+  if (p.tile_count < 0 || p.tile_begin < 0 || p.tile_begin + p.tile_count > m_tiles * n_tiles)
+    return fail("GEMM tile range [%d, +%d) outside the %d tiles", p.tile_begin, p.tile_count, m_tiles * n_tiles);
+  const int groups = std::min(num_sms() / CG, p.tile_count > 0 ? p.tile_count : m_tiles * n_tiles);
   GemmParams q = p;
   q.split = 1;
-  if (EPI == EPI_RESID_F32 && p.flags && g_gemm_split) {
+  if (EPI == EPI_RESID_F32 && p.flags && g_gemm_split && p.tile_count == 0) {
     // partly-filled last wave: cut its tiles along K so that the idle groups take a share (gemm_work_unit)
     const int tiles = m_tiles * n_tiles, rem = tiles % groups;
     if (tiles > groups && rem) q.split = std::min({groups / rem, 4, p.K / kBK / 32, kSplitFlagInts / (rem * CG * kEpiWarps)});
@@ -328,6 +332,8 @@ struct pgibbs_engine {
   pgibbs_model_config cfg;
   int device = 0;
   cudaStream_t stream = nullptr, own_stream = nullptr;
+  cudaStream_t side_stream = nullptr;              // fork / join partner of `stream` (run_gemm_resid_ln)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::map<std::string, std::pair<float*, int64_t>> raw;  // fp32 device copies by state-dict key
   std::vector<void*> owned;                               // packed weight allocations
   std::vector<LayerW> L;
@@ -587,21 +593,34 @@ static int allocate_shape(pgibbs_engine* e, int B, int R, int T) {
 }
 
 // ----------------------------------------------------------------------------- the forward pass
+// LayerNorm of rows [row0, row0 + rows) of x into the same rows of `out` (ungathered), or of the scheduled rows
+// (`gather`).  `dir` < 0: take the next zigzag direction; `st`: stream (default the engine's), `pdl`: programmatic
+// dependent launch allowed (not for a kernel whose predecessor is an event of another stream).
 static int run_ln(pgibbs_engine* e, const float* x, const float* w, const float* b, __half* out, int rows,
-                  const Schedule* gather, int iter) {
+                  const Schedule* gather, int iter, int row0 = 0, int dir = -1, cudaStream_t st = nullptr,
+                  bool pdl = true) {
   LnParams p{};
-  p.x = x; p.w = w; p.b = b; p.out = out; p.rows_out = rows; p.d = e->cfg.embed_dim; p.eps = e->ln_eps;
+  p.d = e->cfg.embed_dim;
+  if (e->precision >= 2) { p.ld_out = 2 * p.d; p.lo_off = p.d; }   // [hi | lo] rows (split-operand mode)
+  p.x = x + static_cast<size_t>(row0) * p.d; p.w = w; p.b = b;
+  p.out = out + static_cast<size_t>(row0) * (p.ld_out ? p.ld_out : p.d);
+  p.rows_out = rows; p.eps = e->ln_eps;
   if (gather) p.sched = *gather; else p.sched.positions = nullptr;
   p.iter = iter; p.T = e->T;
-  p.reverse = gather ? 0 : e->next_dir();
-  if (e->precision >= 2) { p.ld_out = 2 * p.d; p.lo_off = p.d; }   // [hi | lo] rows (split-operand mode)
+  p.reverse = gather ? 0 : dir >= 0 ? dir : e->next_dir();
+  if (rows <= 0) return 0;
   ProfScope ps(e, "layernorm");
   const dim3 grid((rows + 7) / 8);
   const int vpl = (p.d / 4 + 31) / 32;  // float4 vectors per lane
-  if (vpl <= 3) CK(launch_pdl(layernorm_kernel<true, 3>, grid, dim3(256), 0, e->stream, p));
-  else if (vpl <= 6) CK(launch_pdl(layernorm_kernel<true, 6>, grid, dim3(256), 0, e->stream, p));
-  else if (vpl <= 10) CK(launch_pdl(layernorm_kernel<true, 10>, grid, dim3(256), 0, e->stream, p));
-  else CK(launch_pdl(layernorm_kernel<true, kMaxVecPerLane>, grid, dim3(256), 0, e->stream, p));
+  if (!st) st = e->stream;
+  t_no_pdl = !pdl;
+  cudaError_t ce;
+  if (vpl <= 3) ce = launch_pdl(layernorm_kernel<true, 3>, grid, dim3(256), 0, st, p);
+  else if (vpl <= 6) ce = launch_pdl(layernorm_kernel<true, 6>, grid, dim3(256), 0, st, p);
+  else if (vpl <= 10) ce = launch_pdl(layernorm_kernel<true, 10>, grid, dim3(256), 0, st, p);
+  else ce = launch_pdl(layernorm_kernel<true, kMaxVecPerLane>, grid, dim3(256), 0, st, p);
+  t_no_pdl = false;
+  CK(ce);
   return 0;
 }
 
@@ -622,6 +641,54 @@ static int run_gemm(pgibbs_engine* e, const char* name, int epi, GemmPlan g, con
   p.k_segs = e->k_segs();
   ProfScope ps(e, name);
   return launch_gemm(epi, g, a, b, p, e->stream);
+}
+
+// A residual GEMM (x += A W^T + b) followed by the LayerNorm of x into h.  Plain form: the two launches one after the
+// other (PGIBBS_TAIL_OVERLAP=0, profiling, split precision).  Otherwise, with a partly-filled last wave (config 2: 325 tiles on 74 CTA pairs = 4 full waves +
+// 29 tiles, i.e. 60 % of the SMs idle for a fifth of the GEMM) the GEMM is cut at the wave boundary: after the full waves
+// a fork hands the row blocks that are COMPLETE (all their column tiles lie in the full waves) to a LayerNorm on the side
+// stream, which runs on the SMs the last wave leaves idle; the rest of the rows are normalised after the join.  Same
+// kernels, same per-element arithmetic, rows are independent: results are bit-identical to the plain form.  Inside a
+// stream capture the fork / join become parallel branches of the graph.
+static int run_gemm_resid_ln(pgibbs_engine* e, const char* name, GemmPlan g, const CUtensorMap& a, const CUtensorMap& b,
+                             GemmParams p, const float* ln_w, const float* ln_b) {
+  const int M = p.M, rows_per_blk = kBM * g.cg;
+  const int m_tiles = (M + rows_per_blk - 1) / rows_per_blk, n_tiles = (p.N + g.bn - 1) / g.bn;
+  const int tiles = m_tiles * n_tiles, groups = std::min(num_sms() / g.cg, tiles);
+  const int full = tiles / groups * groups, rem = tiles - full;
+  const int done_blks = full / n_tiles;     // row blocks whose every column tile is in the full waves
+  const bool overlap = g_tail_overlap && ln_w && !e->prof && !g_gemm_split && rem > 0 && done_blks > 0 && e->precision == 0;
+  if (!overlap) {
+    TRY(run_gemm(e, name, EPI_RESID_F32, g, a, b, p));
+    if (ln_w) TRY(run_ln(e, e->x, ln_w, ln_b, e->h, M, nullptr, 0));
+    return 0;
+  }
+  if (!e->side_stream) {
+    CK(cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+  }
+  const int gemm_dir = e->next_dir(), ln_dir = e->next_dir();
+  p.flags = e->split_flags; p.reverse = gemm_dir; p.k_segs = e->k_segs();
+  GemmParams pa = p, pb = p;
+  pa.tile_begin = 0; pa.tile_count = full;
+  pb.tile_begin = full; pb.tile_count = rem;
+  // rows of the complete blocks: the first `done_blks` blocks in the GEMM's walking order
+  const int done_rows = std::min(M, done_blks * rows_per_blk);
+  // ascending walk: blocks 0 .. done_blks-1 = rows [0, done_rows); descending walk: the LAST done_blks blocks
+  const int lo = gemm_dir ? std::min(M, (m_tiles - done_blks) * rows_per_blk) : 0;
+  const int hi = gemm_dir ? M : done_rows;
+  { ProfScope ps(e, name); TRY(launch_gemm(EPI_RESID_F32, g, a, b, pa, e->stream)); }
+  CK(cudaEventRecord(e->ev_fork, e->stream));
+  CK(cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
+  TRY(run_ln(e, e->x, ln_w, ln_b, e->h, hi - lo, nullptr, 0, lo, ln_dir, e->side_stream, false));
+  CK(cudaEventRecord(e->ev_join, e->side_stream));
+  { ProfScope ps(e, name); TRY(launch_gemm(EPI_RESID_F32, g, a, b, pb, e->stream)); }
+  CK(cudaStreamWaitEvent(e->stream, e->ev_join, 0));
+  // the rows the last wave was still working on
+  if (gemm_dir) TRY(run_ln(e, e->x, ln_w, ln_b, e->h, lo, nullptr, 0, 0, ln_dir, e->stream, false));
+  else TRY(run_ln(e, e->x, ln_w, ln_b, e->h, M - hi, nullptr, 0, hi, ln_dir, e->stream, false));
+  return 0;
 }
 
 static int launch_attention(const AttnParams& p, int groups, int H, int hd, cudaStream_t st) {
@@ -762,15 +829,14 @@ static int forward(pgibbs_engine* e, const Schedule& sched_in, int n_chains, int
     LayerW& l = e->L[li];
     if (c.arch == PGIBBS_ARCH_MSA) {
       const float row_scale = (1.0f / sqrtf(static_cast<float>(hd))) / sqrtf(static_cast<float>(e->R));
-      // tied row attention
-      TRY(run_ln(e, e->x, l.ln1w, l.ln1b, e->h, M, nullptr, 0));
+      // tied row attention (the first LayerNorm of layers > 0 was issued behind the previous layer's FC2)
+      if (li == 0) TRY(run_ln(e, e->x, l.ln1w, l.ln1b, e->h, M, nullptr, 0));
       GemmParams q = gp(M, 3 * d, d, l.bqkv, e->qkv, 3 * d);
       q.q_cols = d; q.q_scale = row_scale; q.rope_cols = 0; q.head_dim = hd; q.seq_len = e->T;
       TRY(run_gemm(e, "gemm_qkv", EPI_QKV_F16, e->g_qkv, e->m_h, l.m_wqkv, q));
       TRY(run_msa_row_attention(e));
-      TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->g_o, e->m_ctx, l.m_wo, gp(M, d, d, l.bo, e->x, d)));
-      // column attention
-      TRY(run_ln(e, e->x, l.lncw, l.lncb, e->h, M, nullptr, 0));
+      // out-projection, then the column attention's LayerNorm
+      TRY(run_gemm_resid_ln(e, "gemm_out", e->g_o, e->m_ctx, l.m_wo, gp(M, d, d, l.bo, e->x, d), l.lncw, l.lncb));
       // (R == 1: one key per column, softmax = 1, ctx = v -- fair-esm short-cuts this case to Wo(Wv x), same result)
       GemmParams qc = gp(M, 3 * d, d, l.c_bqkv, e->qkv, 3 * d);
       qc.q_cols = d; qc.q_scale = 1.0f / sqrtf(static_cast<float>(hd)); qc.rope_cols = 0; qc.head_dim = hd;
@@ -784,9 +850,9 @@ static int forward(pgibbs_engine* e, const Schedule& sched_in, int n_chains, int
         if (m && *m) return fail("%s", m);
         if (m) TRY(launch_attention(ap, e->B * e->T, c.heads, hd, st));  // shape not covered: generic kernel
       }
-      TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->g_o, e->m_ctx, l.m_cwo, gp(M, d, d, l.c_bo, e->x, d)));
+      TRY(run_gemm_resid_ln(e, "gemm_out", e->g_o, e->m_ctx, l.m_cwo, gp(M, d, d, l.c_bo, e->x, d), l.ln2w, l.ln2b));
     } else {
-      TRY(run_ln(e, e->x, l.ln1w, l.ln1b, e->h, M, nullptr, 0));
+      if (li == 0) TRY(run_ln(e, e->x, l.ln1w, l.ln1b, e->h, M, nullptr, 0));
       GemmParams q = gp(M, 3 * d, d, l.bqkv, e->qkv, 3 * d);
       q.q_cols = d; q.q_scale = 1.0f / sqrtf(static_cast<float>(hd));
       q.rope_cols = c.arch == PGIBBS_ARCH_ESM2 ? 2 * d : 0;
@@ -798,15 +864,17 @@ static int forward(pgibbs_engine* e, const Schedule& sched_in, int n_chains, int
                       e->n_seq, e->T, d));
       }
       TRY(run_attention(e));
-      TRY(run_gemm(e, "gemm_out", EPI_RESID_F32, e->g_o, e->m_ctx, l.m_wo, gp(M, d, d, l.bo, e->x, d)));
+      TRY(run_gemm_resid_ln(e, "gemm_out", e->g_o, e->m_ctx, l.m_wo, gp(M, d, d, l.bo, e->x, d), l.ln2w, l.ln2b));
     }
-    TRY(run_ln(e, e->x, l.ln2w, l.ln2b, e->h, M, nullptr, 0));
     {
       GemmParams f1 = gp(M, F, d, l.b1, e->ffn, e->ak() * F);
       if (e->precision >= 2) f1.lo_off = F;   // ffn rows are [hi | lo]
       TRY(run_gemm(e, "gemm_fc1", EPI_GELU_F16, e->g_fc1, e->m_h, l.m_w1, f1));
     }
-    TRY(run_gemm(e, "gemm_fc2", EPI_RESID_F32, e->g_fc2, e->m_ffn, l.m_w2, gp(M, d, F, l.b2, e->x, d)));
+    // FC2, then the next layer's first LayerNorm (none behind the last layer: the LM head normalises its own rows)
+    const bool more = li + 1 < n_layers;
+    TRY(run_gemm_resid_ln(e, "gemm_fc2", e->g_fc2, e->m_ffn, l.m_w2, gp(M, d, F, l.b2, e->x, d),
+                          more ? e->L[li + 1].ln1w : nullptr, more ? e->L[li + 1].ln1b : nullptr));
   }
   // LM head on the scheduled rows only
   const int rows = n_chains * sched.P;
@@ -978,6 +1046,7 @@ int pgibbs_create(const pgibbs_model_config* cfg, int32_t device_id, pgibbs_engi
   if (const char* f = getenv("PGIBBS_GEMM_CG")) g_force_cg = atoi(f);
   if (const char* f = getenv("PGIBBS_GEMM_SPLIT")) g_gemm_split = atoi(f);
   if (const char* f = getenv("PGIBBS_EPI_DIRECT")) g_epi_direct = atoi(f);
+  if (const char* f = getenv("PGIBBS_TAIL_OVERLAP")) g_tail_overlap = atoi(f);
   if (const char* f = getenv("PGIBBS_PDL")) g_pdl = atoi(f);
   if (const char* f = getenv("PGIBBS_GRAPH")) g_graph = atoi(f);
   if (const char* f = getenv("PGIBBS_ZIGZAG")) g_zigzag = atoi(f);
@@ -1024,6 +1093,9 @@ int pgibbs_destroy(pgibbs_engine* e) {
   cudaFree(e->iter_dev);
   for (auto& t : e->prof_pending) { cudaEventDestroy(std::get<1>(t)); cudaEventDestroy(std::get<2>(t)); }
   for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
+  if (e->side_stream) cudaStreamDestroy(e->side_stream);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
   return 0;

@@ -64,6 +64,11 @@ struct GemmParams {
   // 32-byte loads issued a chunk ahead both measured 17-19 % SLOWER on the out-projection,
   // profiles/r02zzz10_epilogue_direct_ab.txt.)
   int direct;
+  // Sub-range of the launch's tile sequence (position = order in which the static schedule hands tiles out, before the
+  // `reverse` mapping): this launch computes positions [tile_begin, tile_begin + tile_count).  tile_count == 0: all.
+  // The engine cuts a residual GEMM into its full waves and its partly-filled last wave with it (engine.cu:
+  // run_gemm_resid_ln), so that the LayerNorm behind it can start on the finished row blocks meanwhile.
+  int tile_begin, tile_count;
 };
 
 constexpr int kBM = 128;
@@ -419,7 +424,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int group = blockIdx.x / CG, num_groups = gridDim.x / CG;
   const int m_tiles = (p.M + kBM * CG - 1) / (kBM * CG);
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
+  const int total_tiles = m_tiles * n_tiles;
+  const int num_tiles = p.tile_count > 0 ? p.tile_count : total_tiles;   // positions this launch works through
   const int kb_per_seg = p.K / kBK;
   const int num_kb = kb_per_seg * (p.k_segs > 1 ? p.k_segs : 1);   // split-operand mode: 2 or 3 passes over K
   const int split = EPI == EPI_RESID_F32 ? p.split : 1;
@@ -463,7 +469,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t phase = 0;
     WorkUnit u;
     for (int it = 0; gemm_work_unit(it, group, num_groups, num_tiles, num_kb, split, u); ++it) {
-      const int tile = p.reverse ? num_tiles - 1 - u.tile : u.tile;
+      const int tile = p.reverse ? total_tiles - 1 - (u.tile + p.tile_begin) : u.tile + p.tile_begin;
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int a_row = (m_blk * CG + rank) * kBM, b_row = n_blk * BN + rank * kBNL;
       for (int kb = u.kb0; kb < u.kb1; ++kb) {
@@ -543,7 +549,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     int sbuf = 0;
     WorkUnit u;
     for (int it = 0; gemm_work_unit(it, group, num_groups, num_tiles, num_kb, split, u); ++it) {
-      const int tile = p.reverse ? num_tiles - 1 - u.tile : u.tile;
+      const int tile = p.reverse ? total_tiles - 1 - (u.tile + p.tile_begin) : u.tile + p.tile_begin;
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();

@@ -695,6 +695,32 @@ def test_graph_replay_equals_kernel_by_kernel(arch, rng, monkeypatch):
     assert len(set(outs[1])) > 1   # the chains did move
 
 
+@pytest.mark.parametrize("arch,d,H,shape", [("roberta_large", 512, 8, (40, 258)),       # 82 tiles on 74 CTA pairs: 74 + 8
+                                            ("esm2", 512, 8, (41, 257)),
+                                            ("msa_transformer", 768, 12, (4, 20, 129))])  # 123 tiles: 74 + 49
+def test_tail_overlap_bit_identical(arch, d, H, shape, monkeypatch):
+    """PGIBBS_TAIL_OVERLAP=1 cuts every residual GEMM at its last full wave and runs the LayerNorm of the finished row
+    blocks on a second stream next to the partly-filled last wave (fork / join; parallel graph branches under capture).
+    Same kernels on the same rows: logits and a 17-iteration graph-replayed generate must equal the plain order bit for bit."""
+    from protein_gibbs_sampler_b200.config import tiny_config
+    cfg = tiny_config(arch, 3, d, H, 4 * d)
+    tok = _tokens(cfg, shape, 21)
+    logits, seqs = [], []
+    for mode in ("0", "1"):
+        monkeypatch.setenv("PGIBBS_TAIL_OVERLAP", mode)
+        s, _ = make(cfg, 9)
+        logits.append(s.model.model(tok)["logits"])
+        if arch != "msa_transformer":
+            rnd = random.Random(3)
+            seq = "".join(rnd.choice("ACDEFGHIKLMNPQRSTVWY") for _ in range(shape[1] - 2))
+            random.seed(4); torch.manual_seed(4)
+            seqs.append(s.generate(shape[0], seq, batch_size=shape[0], num_iters=17, burnin=5, top_k=3, num_positions=9,
+                                   show_progress_bar=False))
+    assert bool(torch.isfinite(logits[0]).all()) and torch.equal(logits[0], logits[1])
+    if seqs:
+        assert seqs[0] == seqs[1] and len(set(seqs[1])) > 1
+
+
 # ----------------------------------------------------------------- full-size properties of the other BASELINE configs
 def _full_size_properties(sampler, toks, plan, rows_per_unit, valid_hi, units_sub, **run_kw):
     """Determinism, only scheduled positions change, only valid residues are written, and a sub-batch of chains /
