@@ -40,7 +40,9 @@ const char* pgibbs_version(void);
 int pgibbs_create(const pgibbs_model_config* cfg, int32_t device_id, pgibbs_engine** out);
 int pgibbs_destroy(pgibbs_engine* e);
 /* external != 0: launch on the caller's CUDA stream `cuda_stream` (a cudaStream_t; NULL is the CUDA default
- * stream).  external == 0: back to the engine's own non-blocking stream. */
+ * stream).  external == 0: back to the engine's own non-blocking stream.  Inside a forward the engine may fork part of
+ * the work to a private second stream (LayerNorm next to a GEMM's last wave); every fork is joined back on THIS stream
+ * before the next dependent kernel, so stream order as seen by the caller is unchanged. */
 int pgibbs_set_stream(pgibbs_engine* e, void* cuda_stream, int32_t external);
 
 /* One fp32 tensor of the fair-esm state dict by key name (models.py:61-86 bind the loaders). */

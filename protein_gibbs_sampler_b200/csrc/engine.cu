@@ -1,5 +1,6 @@
 // pgibbs engine: host-side orchestration of the on-device Gibbs step + the C ABI (include/pgibbs.h).
-// One engine per GPU.  All work is queued on one CUDA stream; nothing between iterations touches the host.
+// One engine per GPU.  All work is queued on one CUDA stream (plus a private side stream that run_gemm_resid_ln forks
+// to and joins back from inside a layer); nothing between iterations touches the host.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
