@@ -110,6 +110,11 @@ int pgibbs_sync(pgibbs_engine* e);
 
 /* Debug/parity taps: copy an internal activation buffer ("x", "h", "qkv", "ctx", "ffn", "g") as fp32. */
 int pgibbs_debug_read(pgibbs_engine* e, const char* which, float* out, int64_t numel);
+/* Host arithmetic only (no GPU): where the engine cuts a residual GEMM of M x N outputs tiled (128 * cta_group) x block_n
+ * on `sms` SMs so that the following LayerNorm can start next to the partly-filled last wave.
+ * out4 = {tiles in the full waves, tiles in the last wave, first row, one-past-last row of the finished row blocks}. */
+int pgibbs_debug_tail_plan(int32_t M, int32_t N, int32_t block_n, int32_t cta_group, int32_t sms, int32_t reverse,
+                           int32_t* out4);
 /* Stop the forward after `n_layers` transformer layers (negative = all); parity bisecting only. */
 int pgibbs_debug_layer_limit(pgibbs_engine* e, int32_t n_layers);
 

@@ -43,6 +43,7 @@ SIGNATURES = {
     "pgibbs_score": (c_i32, [c_void_p, c_void_p, c_i32, c_i32, c_void_p]),
     "pgibbs_sync": (c_i32, [c_void_p]),
     "pgibbs_debug_read": (c_i32, [c_void_p, c_char_p, c_void_p, c_i64]),
+    "pgibbs_debug_tail_plan": (c_i32, [c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, P(c_i32)]),
     "pgibbs_debug_layer_limit": (c_i32, [c_void_p, c_i32]),
     "pgibbs_profile_enable": (c_i32, [c_void_p, c_i32]),
     "pgibbs_profile_read": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, P(c_i32)]),

@@ -651,14 +651,31 @@ static int run_gemm(pgibbs_engine* e, const char* name, int epi, GemmPlan g, con
 // stream, which runs on the SMs the last wave leaves idle; the rest of the rows are normalised after the join.  Same
 // kernels, same per-element arithmetic, rows are independent: results are bit-identical to the plain form.  Inside a
 // stream capture the fork / join become parallel branches of the graph.
+// Where a GEMM of M x N outputs is cut: `full` tiles (whole waves of `groups` CTA groups) + `rem` tiles, and the rows
+// [lo, hi) of the row blocks whose EVERY column tile lies in the full waves (tile sequence: n fastest, walked from the
+// last tile down when `reverse`).  Pure arithmetic (pgibbs_debug_tail_plan exposes it to the CPU tests).
+struct TailPlan { int full, rem, lo, hi; };
+static TailPlan tail_plan(int M, int N, int bn, int cg, int sms, int reverse) {
+  const int rows_per_blk = kBM * cg;
+  const int m_tiles = (M + rows_per_blk - 1) / rows_per_blk, n_tiles = (N + bn - 1) / bn;
+  const int tiles = m_tiles * n_tiles, groups = std::max(1, std::min(sms / cg, tiles));
+  TailPlan t{};
+  t.full = tiles / groups * groups;
+  t.rem = tiles - t.full;
+  const int done_blks = t.full / n_tiles;     // row blocks whose every column tile is in the full waves
+  // ascending walk: blocks 0 .. done_blks-1 = rows [0, done_blks * rows_per_blk); descending walk: the LAST done_blks blocks
+  t.lo = reverse ? std::min(M, (m_tiles - done_blks) * rows_per_blk) : 0;
+  t.hi = reverse ? M : std::min(M, done_blks * rows_per_blk);
+  if (done_blks == 0) t.lo = t.hi = 0;
+  return t;
+}
+
 static int run_gemm_resid_ln(pgibbs_engine* e, const char* name, GemmPlan g, const CUtensorMap& a, const CUtensorMap& b,
                              GemmParams p, const float* ln_w, const float* ln_b) {
-  const int M = p.M, rows_per_blk = kBM * g.cg;
-  const int m_tiles = (M + rows_per_blk - 1) / rows_per_blk, n_tiles = (p.N + g.bn - 1) / g.bn;
-  const int tiles = m_tiles * n_tiles, groups = std::min(num_sms() / g.cg, tiles);
-  const int full = tiles / groups * groups, rem = tiles - full;
-  const int done_blks = full / n_tiles;     // row blocks whose every column tile is in the full waves
-  const bool overlap = g_tail_overlap && ln_w && !e->prof && !g_gemm_split && rem > 0 && done_blks > 0 && e->precision == 0;
+  const int M = p.M;
+  const TailPlan probe = tail_plan(M, p.N, g.bn, g.cg, num_sms(), 0);
+  const bool overlap = g_tail_overlap && ln_w && !e->prof && !g_gemm_split && probe.rem > 0 && probe.hi > probe.lo &&
+                       e->precision == 0;
   if (!overlap) {
     TRY(run_gemm(e, name, EPI_RESID_F32, g, a, b, p));
     if (ln_w) TRY(run_ln(e, e->x, ln_w, ln_b, e->h, M, nullptr, 0));
@@ -671,14 +688,11 @@ static int run_gemm_resid_ln(pgibbs_engine* e, const char* name, GemmPlan g, con
   }
   const int gemm_dir = e->next_dir(), ln_dir = e->next_dir();
   p.flags = e->split_flags; p.reverse = gemm_dir; p.k_segs = e->k_segs();
+  const TailPlan t = tail_plan(M, p.N, g.bn, g.cg, num_sms(), gemm_dir);
   GemmParams pa = p, pb = p;
-  pa.tile_begin = 0; pa.tile_count = full;
-  pb.tile_begin = full; pb.tile_count = rem;
-  // rows of the complete blocks: the first `done_blks` blocks in the GEMM's walking order
-  const int done_rows = std::min(M, done_blks * rows_per_blk);
-  // ascending walk: blocks 0 .. done_blks-1 = rows [0, done_rows); descending walk: the LAST done_blks blocks
-  const int lo = gemm_dir ? std::min(M, (m_tiles - done_blks) * rows_per_blk) : 0;
-  const int hi = gemm_dir ? M : done_rows;
+  pa.tile_begin = 0; pa.tile_count = t.full;
+  pb.tile_begin = t.full; pb.tile_count = t.rem;
+  const int lo = t.lo, hi = t.hi;   // rows of the complete blocks
   { ProfScope ps(e, name); TRY(launch_gemm(EPI_RESID_F32, g, a, b, pa, e->stream)); }
   CK(cudaEventRecord(e->ev_fork, e->stream));
   CK(cudaStreamWaitEvent(e->side_stream, e->ev_fork, 0));
@@ -1387,6 +1401,15 @@ int pgibbs_debug_read(pgibbs_engine* e, const char* which, float* out, int64_t n
     cudaFree(tmp);
     if (er != cudaSuccess) return fail("debug read failed: %s", cudaGetErrorString(er));
   }
+  return 0;
+}
+
+int pgibbs_debug_tail_plan(int32_t M, int32_t N, int32_t block_n, int32_t cta_group, int32_t sms, int32_t reverse,
+                           int32_t* out4) {
+  if (M <= 0 || N <= 0 || block_n <= 0 || (cta_group != 1 && cta_group != 2) || sms < cta_group || !out4)
+    return fail("pgibbs_debug_tail_plan: invalid arguments");
+  const TailPlan t = tail_plan(M, N, block_n, cta_group, sms, reverse);
+  out4[0] = t.full; out4[1] = t.rem; out4[2] = t.lo; out4[3] = t.hi;
   return 0;
 }
 

@@ -88,6 +88,40 @@ def test_gemm_accumulator_handback_carries_no_gpu_fence():
         assert any(o.startswith("UTCHMMA") for o in ops), k
 
 
+def test_tail_plan_matches_brute_force():
+    """Where the engine cuts a residual GEMM for the LayerNorm overlap (engine.cu: tail_plan, through the host-only
+    pgibbs_debug_tail_plan): the rows handed to the early LayerNorm must be exactly the row blocks whose every column tile
+    lies in the full waves -- in both walking directions -- and the last wave must not touch them."""
+    lib = _lib.load()
+    out = (ctypes.c_int32 * 4)()
+    cases = [(16512, 1280, 256, 2), (16512, 1280, 256, 1), (32896, 1280, 256, 2), (66048, 768, 256, 2), (10320, 512, 256, 2),
+             (10537, 512, 128, 2), (10320, 768, 192, 2), (5000, 320, 64, 1), (258, 1280, 256, 2), (18944, 1280, 256, 2),
+             (16384, 1280, 128, 1), (40000, 2560, 256, 2)]
+    seen_overlap = 0
+    for M, N, bn, cg in cases:
+        for sms in (148, 132):
+            for rev in (0, 1):
+                _lib.check(lib.pgibbs_debug_tail_plan(M, N, bn, cg, sms, rev, out))
+                full, rem, lo, hi = list(out)
+                rpb = 128 * cg
+                m_tiles, n_tiles = -(-M // rpb), -(-N // bn)
+                tiles, groups = m_tiles * n_tiles, min(sms // cg, m_tiles * n_tiles)
+                assert full + rem == tiles and full % groups == 0 and 0 <= rem < groups
+                blk = lambda pos: ((tiles - 1 - pos) if rev else pos) // n_tiles
+                count = {}
+                for pos in range(full):
+                    count[blk(pos)] = count.get(blk(pos), 0) + 1
+                done = sorted(b for b, c in count.items() if c == n_tiles)
+                rows = set()
+                for b in done:
+                    rows.update(range(b * rpb, min(M, (b + 1) * rpb)))
+                assert rows == set(range(lo, hi)), (M, N, bn, cg, sms, rev, lo, hi)
+                assert not any(blk(pos) in set(done) for pos in range(full, tiles))
+                seen_overlap += bool(rem and done)
+    assert seen_overlap >= 20
+    assert lib.pgibbs_debug_tail_plan(0, 1280, 256, 2, 148, 0, out) != 0
+
+
 def test_create_fails_loudly_without_gpu():
     lib = _lib.load()
     cfg = _lib.ModelConfig(arch=1, layers=1, embed_dim=64, heads=2, ffn_dim=128, vocab=33, max_positions=1024,
