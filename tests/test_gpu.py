@@ -103,7 +103,8 @@ def test_gemm_output_paths_bit_identical(M, N, K, bn, monkeypatch):
         monkeypatch.setenv("PGIBBS_EPI_DIRECT", "0")
         staged = op_gemm(A, B, bias, epilogue=epi, block_n=bn)
         assert torch.equal(direct, staged), "epilogue %d" % epi
-    monkeypatch.delenv("PGIBBS_EPI_DIRECT")
+    monkeypatch.setenv("PGIBBS_EPI_DIRECT", "6")
+    op_gemm(A[:128], B, bias, epilogue=0, block_n=bn)     # leaves the process-wide switch at its default (direct) again
 
 
 def test_gemm_operator_config2_rows_vs_torch():
