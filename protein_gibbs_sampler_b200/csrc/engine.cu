@@ -644,13 +644,6 @@ static int run_gemm(pgibbs_engine* e, const char* name, int epi, GemmPlan g, con
   return launch_gemm(epi, g, a, b, p, e->stream);
 }
 
-// A residual GEMM (x += A W^T + b) followed by the LayerNorm of x into h.  Plain form: the two launches one after the
-// other (PGIBBS_TAIL_OVERLAP=0, profiling, split precision).  Otherwise, with a partly-filled last wave (config 2: 325 tiles on 74 CTA pairs = 4 full waves +
-// 29 tiles, i.e. 60 % of the SMs idle for a fifth of the GEMM) the GEMM is cut at the wave boundary: after the full waves
-// a fork hands the row blocks that are COMPLETE (all their column tiles lie in the full waves) to a LayerNorm on the side
-// stream, which runs on the SMs the last wave leaves idle; the rest of the rows are normalised after the join.  Same
-// kernels, same per-element arithmetic, rows are independent: results are bit-identical to the plain form.  Inside a
-// stream capture the fork / join become parallel branches of the graph.
 // Where a GEMM of M x N outputs is cut: `full` tiles (whole waves of `groups` CTA groups) + `rem` tiles, and the rows
 // [lo, hi) of the row blocks whose EVERY column tile lies in the full waves (tile sequence: n fastest, walked from the
 // last tile down when `reverse`).  Pure arithmetic (pgibbs_debug_tail_plan exposes it to the CPU tests).
@@ -670,6 +663,13 @@ static TailPlan tail_plan(int M, int N, int bn, int cg, int sms, int reverse) {
   return t;
 }
 
+// A residual GEMM (x += A W^T + b) followed by the LayerNorm of x into h.  Plain form: the two launches one after the
+// other (PGIBBS_TAIL_OVERLAP=0, profiling, split precision).  Otherwise, with a partly-filled last wave (config 2: 325 tiles on 74 CTA pairs = 4 full waves +
+// 29 tiles, i.e. 60 % of the SMs idle for a fifth of the GEMM) the GEMM is cut at the wave boundary: after the full waves
+// a fork hands the row blocks that are COMPLETE (all their column tiles lie in the full waves) to a LayerNorm on the side
+// stream, which runs on the SMs the last wave leaves idle; the rest of the rows are normalised after the join.  Same
+// kernels, same per-element arithmetic, rows are independent: results are bit-identical to the plain form.  Inside a
+// stream capture the fork / join become parallel branches of the graph.
 static int run_gemm_resid_ln(pgibbs_engine* e, const char* name, GemmPlan g, const CUtensorMap& a, const CUtensorMap& b,
                              GemmParams p, const float* ln_w, const float* ln_b) {
   const int M = p.M;
