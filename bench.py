@@ -42,6 +42,8 @@ def workload_config(n_gpus):
         "l2": "no flush: per-iteration working set (1.3 GB fp16 weights + >1 GB activations) >> 126 MB L2",
         "weights": "synthetic seeded N(0,0.02) (no pretrained checkpoints offline)",
         "precision": "fast (one tensor-core pass of fp16 operands per GEMM); split-operand mode under other_configs",
+        "launch": "one stream, programmatic dependent launch, CUDA-graph replay from the 2nd iteration of a run, LayerNorm "
+                  "forked next to the residual GEMMs' last wave (switches: PGIBBS_PDL / PGIBBS_GRAPH / PGIBBS_TAIL_OVERLAP)",
     }
 
 
